@@ -1,0 +1,450 @@
+// sm_100a kernels of RendererCUDA.  One render pass = 5 launches:
+//   sglVertexKernel   vertex shading + clip mask + perspective divide + viewport, one thread per VAO vertex
+//   sglSetupKernel    assembly, clipping (VS re-execution), culling, primitive setup, tile counting
+//   sglTileScanKernel exclusive scan of per-tile counts (single CTA)
+//   sglBinFillKernel  scatter primitive slots into per-tile lists
+//   sglRasterKernel   one CTA per 16x16 screen tile: order-sort the tile's list in shared memory, per-pixel
+//                     coverage/depth in registers, deferred shading, blend, MSAA resolve, write-back
+#pragma once
+#include <cuda_runtime.h>
+#include "sgl_pixel.h"
+
+#ifndef SGL_RASTER_ONLY
+// ---------------------------------------------------------------------------------------------------------
+struct SglSetupShared {
+  uint32_t *tileCount;
+  uint32_t *bigList;
+  uint32_t *bigCount;
+  uint32_t bigCapacity;
+  unsigned long long *counters;
+  int tilesX, tilesY, fbW, fbH;
+  const uint8_t *tileOwner;
+  int rank;
+};
+
+// tile rectangle of a primitive (clamped to the framebuffer); false if empty
+__device__ __forceinline__ bool sglPrimTiles(const SglPrim &p, int fbW, int fbH, int &tx0, int &ty0, int &tx1, int &ty1) {
+  int x0 = p.bx0 < 0 ? 0 : p.bx0, y0 = p.by0 < 0 ? 0 : p.by0;
+  int x1 = p.bx1 >= fbW ? fbW - 1 : p.bx1, y1 = p.by1 >= fbH ? fbH - 1 : p.by1;
+  if (x1 < x0 || y1 < y0) return false;
+  tx0 = x0 / SGL_TILE; ty0 = y0 / SGL_TILE; tx1 = x1 / SGL_TILE; ty1 = y1 / SGL_TILE;
+  return true;
+}
+
+struct SglDeviceAlloc {
+  SglSetupShared S;
+  __device__ int newVertex(const SglDrawRec &d) {
+    int extra = atomicAdd(d.vertexCounter, 1);
+    int idx = d.vertexCount + extra;
+    return idx < d.vertexCap ? idx : -1;
+  }
+  __device__ int newAppendSlots(const SglDrawRec &d, int n) {
+    int a = atomicAdd(d.appendCounter, n);
+    return a + n <= d.appendCap ? d.appendBase + a : -1;
+  }
+  __device__ void overflow() { atomicAdd(S.counters + 7, 1ull); }
+  __device__ void binPrim(int slot, const SglPrim &p) {
+    int tx0, ty0, tx1, ty1;
+    if (!sglPrimTiles(p, S.fbW, S.fbH, tx0, ty0, tx1, ty1)) return;
+    int n = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+    if (n > SGL_BIG_PRIM_TILES) {
+      uint32_t b = atomicAdd(S.bigCount, 1u);
+      if (b < S.bigCapacity) S.bigList[b] = (uint32_t) slot;
+      return;
+    }
+    for (int ty = ty0; ty <= ty1; ty++)
+      for (int tx = tx0; tx <= tx1; tx++) {
+        int t = ty * S.tilesX + tx;
+        if (S.tileOwner && S.tileOwner[t] != S.rank) continue;
+        atomicAdd(&S.tileCount[t], 1u);
+      }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// processVertexShader + perspective divide + viewport transform (RendererSoft.cpp:170-190,259-275,971-992)
+// grid = (ceil(maxVertices/128), drawCount); vertex loads are 4 x LDG.128 (64-byte Vertex, Model.h:20-25)
+__global__ void __launch_bounds__(128) sglVertexKernel(const SglDrawRec *draws) {
+  const SglDrawRec &d = draws[blockIdx.y];
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= d.vertexCount) return;
+  const float4 *src = reinterpret_cast<const float4 *>(d.vertexIn) + (size_t) v * 4;
+  float attr[16];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    float4 q = __ldg(src + i);
+    attr[4 * i] = q.x; attr[4 * i + 1] = q.y; attr[4 * i + 2] = q.z; attr[4 * i + 3] = q.w;
+  }
+  float vary[32];
+  V4 clip = sglVertexShader(d, attr, vary);
+  float4 *vo = reinterpret_cast<float4 *>(d.varyings + (size_t) v * d.varyingStride);
+  for (int k = 0; k < d.varyingStride / 4; k++) vo[k] = make_float4(vary[4 * k], vary[4 * k + 1], vary[4 * k + 2], vary[4 * k + 3]);
+  reinterpret_cast<float4 *>(d.clipPos)[v] = make_float4(clip.x, clip.y, clip.z, clip.w);
+  d.clipMask[v] = sglClipMask(clip);
+  V4 f = sglToScreen(clip, d.vpX, d.vpY, d.vpW, d.vpH);
+  reinterpret_cast<float4 *>(d.fragPos)[v] = make_float4(f.x, f.y, f.z, f.w);
+}
+
+// grid = (ceil(maxInputPrims/128), drawCount)
+__global__ void __launch_bounds__(128) sglSetupKernel(const SglDrawRec *draws, SglSetupOut out, SglSetupShared S, int hasDepth) {
+  const SglDrawRec &d = draws[blockIdx.y];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.inputPrims) return;
+  SglDeviceAlloc alloc;
+  alloc.S = S;
+  sglProcessInputPrim(d, blockIdx.y, i, hasDepth != 0, out, alloc);
+  if (i == 0) atomicAdd(S.counters + 2, (unsigned long long) d.inputPrims);
+}
+
+// single CTA: tileOffset = exclusive scan(tileCount); tileOffset[nTiles] = total (clamped entries are dropped later)
+__global__ void __launch_bounds__(1024) sglTileScanKernel(const uint32_t *tileCount, uint32_t *tileOffset, int nTiles,
+                                                         unsigned long long *counters) {
+  __shared__ uint32_t sWarp[32];
+  __shared__ uint32_t sCarry;
+  if (threadIdx.x == 0) sCarry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < nTiles; base += 1024) {
+    int i = base + threadIdx.x;
+    uint32_t v = i < nTiles ? tileCount[i] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) sWarp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = sWarp[lane];
+      uint32_t winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+      }
+      sWarp[lane] = winc - w;   // exclusive
+    }
+    __syncthreads();
+    uint32_t carry = sCarry;
+    uint32_t excl = carry + sWarp[warp] + inc - v;
+    if (i < nTiles) tileOffset[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) sCarry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    tileOffset[nTiles] = sCarry;
+    atomicAdd(counters + 3, (unsigned long long) sCarry);
+  }
+}
+
+// grid = (ceil(maxSlotsPerDraw/256), drawCount): one thread per primitive slot (originals, then appended)
+__global__ void __launch_bounds__(256) sglBinFillKernel(SglPassParams P) {
+  const SglDrawRec &d = P.draws[blockIdx.y];
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int originals = d.inputPrims * d.slotsPerPrim;
+  int slot;
+  if (j < originals) slot = d.primBase + j;
+  else {
+    int a = j - originals;
+    int used = *d.appendCounter;
+    if (used > d.appendCap) used = d.appendCap;
+    if (a >= used) return;
+    slot = d.appendBase + a;
+  }
+  const SglPrim p = P.prims[slot];
+  if (!(p.flags & SGL_PF_VALID)) return;
+  int tx0, ty0, tx1, ty1;
+  if (!sglPrimTiles(p, P.fbW, P.fbH, tx0, ty0, tx1, ty1)) return;
+  int n = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+  if (n > SGL_BIG_PRIM_TILES) return;   // lives in the pass-wide big list (bigCapacity >= primSlots, never overflows)
+  for (int ty = ty0; ty <= ty1; ty++)
+    for (int tx = tx0; tx <= tx1; tx++) {
+      int t = ty * P.tilesX + tx;
+      if (P.tileOwner && P.tileOwner[t] != P.rank) continue;
+      uint32_t pos = P.tileOffset[t] + atomicAdd(&P.tileCursor[t], 1u);
+      if (pos < P.binCapacity) P.binSlots[pos] = (uint32_t) slot;
+    }
+}
+
+#endif  // SGL_RASTER_ONLY
+
+// ---------------------------------------------------------------------------------------------------------
+#define SGL_SORT_CAP 2048
+#define SGL_PRIM_BATCH 64
+
+__device__ __forceinline__ void sglBitonicSort(uint32_t *keys, uint32_t *vals, int n /* power of two */) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          uint32_t a = keys[i], b = keys[ixj];
+          bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            keys[i] = b; keys[ixj] = a;
+            uint32_t t = vals[i]; vals[i] = vals[ixj]; vals[ixj] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template<int NS>
+__global__ void __launch_bounds__(SGL_TILE_THREADS) sglRasterKernel(SglPassParams P) {
+  __shared__ uint32_t sKeys[SGL_SORT_CAP];
+  __shared__ uint32_t sSlots[SGL_SORT_CAP];
+  __shared__ __align__(16) SglPrim sPrims[SGL_PRIM_BATCH];
+  __shared__ int sCount;
+  __shared__ unsigned int sShaded;
+
+  const int tile = blockIdx.x;
+  if (P.tileOwner && P.tileOwner[tile] != P.rank) return;
+  const int tx = tile % P.tilesX, ty = tile / P.tilesX;
+  const int tid = threadIdx.x;
+  const int px = tx * SGL_TILE + (tid & (SGL_TILE - 1));
+  const int py = ty * SGL_TILE + (tid / SGL_TILE);
+  const bool inFb = px < P.fbW && py < P.fbH;
+  const bool hasColor = P.colorBase != nullptr, hasDepth = P.depthBase != nullptr;
+  const size_t pix = (size_t) py * P.fbW + px;
+
+  SglPixelState<NS> st;
+#pragma unroll
+  for (int s = 0; s < NS; s++) { st.depth[s] = P.clearDepth; st.color[s] = P.clearColor; st.owner[s] = SGL_OWNER_NONE; }
+  if (inFb) {
+    if (hasDepth && !P.clearDepthFlag) {
+      if (NS == 4) {
+        float4 dq = reinterpret_cast<const float4 *>(P.depthBase)[pix];
+        st.depth[0] = dq.x; st.depth[NS > 1 ? 1 : 0] = dq.y; st.depth[NS > 2 ? 2 : 0] = dq.z; st.depth[NS > 3 ? 3 : 0] = dq.w;
+      } else st.depth[0] = P.depthBase[pix];
+    }
+    if (hasColor && !P.clearColorFlag) {
+      if (NS == 4) {
+        uint4 cq = reinterpret_cast<const uint4 *>(P.colorBase)[pix];
+        st.color[0] = cq.x; st.color[NS > 1 ? 1 : 0] = cq.y; st.color[NS > 2 ? 2 : 0] = cq.z; st.color[NS > 3 ? 3 : 0] = cq.w;
+      } else st.color[0] = reinterpret_cast<const uint32_t *>(P.colorBase)[pix];
+    }
+  }
+
+  const uint32_t off = P.tileOffset[tile];
+  uint32_t nList = P.tileOffset[tile + 1] - off;
+  if (off + nList > P.binCapacity) nList = off < P.binCapacity ? P.binCapacity - off : 0;
+  uint32_t nBig = *P.bigCount;
+  if (nBig > P.bigCapacity) nBig = P.bigCapacity;
+  const int tx0 = tx * SGL_TILE, ty0 = ty * SGL_TILE, tx1 = tx0 + SGL_TILE - 1, ty1 = ty0 + SGL_TILE - 1;
+  unsigned int shaded = 0;
+
+  // key windows: the common case (everything fits) is one window covering all keys
+  uint32_t lo = 0;
+  const uint32_t keyEnd = 0xFFFFFFFFu;
+  bool fits = (nList + nBig) <= SGL_SORT_CAP;
+  while (true) {
+    uint32_t hi = keyEnd;
+    // ---- gather candidates with lo <= key < hi
+    while (true) {
+      if (tid == 0) sCount = 0;
+      __syncthreads();
+      for (uint32_t i = tid; i < nList; i += SGL_TILE_THREADS) {
+        uint32_t slot = P.binSlots[off + i];
+        uint32_t key = P.primKeys[slot];
+        if (key >= lo && key < hi) {
+          int idx = atomicAdd(&sCount, 1);
+          if (idx < SGL_SORT_CAP) { sKeys[idx] = key; sSlots[idx] = slot; }
+        }
+      }
+      for (uint32_t i = tid; i < nBig; i += SGL_TILE_THREADS) {
+        uint32_t slot = P.bigList[i];
+        uint32_t key = P.primKeys[slot];
+        if (key >= lo && key < hi) {
+          const SglPrim &bp = P.prims[slot];
+          if (bp.bx0 <= tx1 && bp.bx1 >= tx0 && bp.by0 <= ty1 && bp.by1 >= ty0) {
+            int idx = atomicAdd(&sCount, 1);
+            if (idx < SGL_SORT_CAP) { sKeys[idx] = key; sSlots[idx] = slot; }
+          }
+        }
+      }
+      __syncthreads();
+      if (sCount <= SGL_SORT_CAP) break;
+      hi = lo + (hi - lo) / 2;          // too many: halve the key window and retry
+      __syncthreads();
+    }
+    const int n = sCount;
+    if (n > 1) {
+      int n2 = 1;
+      while (n2 < n) n2 <<= 1;
+      for (int i = n + tid; i < n2; i += SGL_TILE_THREADS) { sKeys[i] = 0xFFFFFFFFu; sSlots[i] = 0; }
+      __syncthreads();
+      sglBitonicSort(sKeys, sSlots, n2);
+    }
+    // ---- process in order
+    for (int b0 = 0; b0 < n; b0 += SGL_PRIM_BATCH) {
+      int nb = n - b0 < SGL_PRIM_BATCH ? n - b0 : SGL_PRIM_BATCH;
+      __syncthreads();
+      {  // 64 records x 4 x uint4 = one 16-byte load per thread
+        int r = tid >> 2, q = tid & 3;
+        if (r < nb) {
+          const uint4 *src = reinterpret_cast<const uint4 *>(P.prims + sSlots[b0 + r]);
+          reinterpret_cast<uint4 *>(sPrims + r)[q] = __ldg(src + q);
+        }
+      }
+      __syncthreads();
+      if (inFb) {
+        for (int k = 0; k < nb; k++) sglPixelPrim<NS>(P, sPrims[k], sSlots[b0 + k], px, py, st, hasColor, hasDepth);
+      }
+    }
+    __syncthreads();
+    if (fits || hi == keyEnd) break;
+    lo = hi;
+  }
+
+  // ---- deferred shading, warp-coherent by draw: lanes shade together when their pending owner is in the draw
+  //      of the warp's smallest pending slot (slots are laid out draw by draw)
+  if (hasColor) {
+    while (true) {
+      // pick this lane's pending owner with the smallest slot
+      uint32_t best = SGL_OWNER_NONE, bestSlot = 0xFFFFFFFFu;
+#pragma unroll
+      for (int s = 0; s < NS; s++) {
+        uint32_t o = st.owner[s];
+        if (o != SGL_OWNER_NONE && (o & 0x1fffffffu) < bestSlot) { best = o; bestSlot = o & 0x1fffffffu; }
+      }
+      uint32_t wmin = __reduce_min_sync(0xffffffffu, bestSlot);
+      if (wmin == 0xFFFFFFFFu) break;
+      uint32_t wdraw = P.prims[wmin].draw;
+      if (best != SGL_OWNER_NONE && P.prims[bestSlot].draw == wdraw) {
+        uint32_t c = sglPackColor(sglShadeSlot<NS>(P, bestSlot, (int) (best >> 29), px, py));
+        shaded++;
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+          if (st.owner[s] == best) { st.color[s] = c; st.owner[s] = SGL_OWNER_NONE; }
+      }
+    }
+  }
+
+  // ---- write-back: per-sample colour/depth and the resolved colour (multiSampleResolve, RendererSoft.cpp:880-912)
+  if (inFb) {
+    if (hasDepth) {
+      if (NS == 4) reinterpret_cast<float4 *>(P.depthBase)[pix] =
+          make_float4(st.depth[0], st.depth[NS > 1 ? 1 : 0], st.depth[NS > 2 ? 2 : 0], st.depth[NS > 3 ? 3 : 0]);
+      else P.depthBase[pix] = st.depth[0];
+    }
+    if (hasColor) {
+      if (NS == 4) {
+        reinterpret_cast<uint4 *>(P.colorBase)[pix] =
+            make_uint4(st.color[0], st.color[NS > 1 ? 1 : 0], st.color[NS > 2 ? 2 : 0], st.color[NS > 3 ? 3 : 0]);
+        if (P.resolveBase) {
+          uint32_t r = 0;
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            uint32_t sum = 0;
+#pragma unroll
+            for (int s = 0; s < NS; s++) sum += (st.color[s] >> (8 * c)) & 0xffu;
+            r |= (sum / NS) << (8 * c);     // u8vec4(sum / 4.f) truncation: exact integer division
+          }
+          reinterpret_cast<uint32_t *>(P.resolveBase)[pix] = r;
+        }
+      } else {
+        reinterpret_cast<uint32_t *>(P.colorBase)[pix] = st.color[0];
+      }
+    }
+  }
+  // counters: one atomic per CTA
+  if (tid == 0) sShaded = 0;
+  __syncthreads();
+  shaded = __reduce_add_sync(0xffffffffu, shaded);
+  if ((tid & 31) == 0 && shaded) atomicAdd(&sShaded, shaded);
+  __syncthreads();
+  if (tid == 0 && sShaded) atomicAdd(P.counters + 4, (unsigned long long) sShaded);
+}
+
+#ifndef SGL_RASTER_ONLY
+// ---------------------------------------------------------------------------------------------------------
+// mip generation: BaseSampler::sampleBufferBilinear (SamplerSoft.h:241-252), one thread per output texel
+__global__ void sglMipKernel(SglTexObj tex, int layer, int level) {
+  int ow = sglLevelDim(tex.width, level), oh = sglLevelDim(tex.height, level);
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= ow || y >= oh) return;
+  int iw = sglLevelDim(tex.width, level - 1), ih = sglLevelDim(tex.height, level - 1);
+  float rx = xdiv((float) iw, (float) ow), ry = xdiv((float) ih, (float) oh);
+  float u = xadd(xmul((float) x, rx), xmul(0.5f, rx)), v = xadd(xmul((float) y, ry), xmul(0.5f, ry));
+  SglSampler s;
+  s.tex = &tex;
+  s.filter = SGL_FILTER_LINEAR;
+  s.wrap = SGL_WRAP_CLAMP_TO_EDGE;
+  s.border = 0;
+  uint32_t t = sglPixelBilinear(s, layer, level - 1, u, v);
+  uint32_t *dst = (uint32_t *) (tex.base + (size_t) layer * tex.layerStride + tex.levelOffset[level]);
+  dst[sglTexelIndex(tex.layout, ow, x, y)] = t;
+}
+
+// linear host image <-> texture layout (upload / read-back of Tiled and Morton textures)
+__global__ void sglRelayoutKernel(uint32_t *dst, const uint32_t *src, int w, int h, int layout, int toLayout) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  size_t lin = (size_t) y * w + x, til = sglTexelIndex(layout, w, x, y);
+  if (toLayout) dst[til] = src[lin];
+  else dst[lin] = src[til];
+}
+
+__global__ void sglFill32Kernel(uint32_t *dst, uint32_t value, size_t n) {
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = value;
+}
+
+// ---- known-answer-test kernels (wrap the device functions above) ---------------------------------------------
+__global__ void sglKatBarycentricKernel(const float *tri, const float *xy, int n, float *bcOut, int *insideOut, float *zwOut) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  SglPrim p;
+  for (int v = 0; v < 3; v++)
+    for (int c = 0; c < 4; c++) p.v[v][c] = tri[v * 4 + c];
+  SglTriEdge e = sglTriEdge(p);
+  float b0 = 0, b1 = 0, b2 = 0;
+  bool in = false;
+  if (!(fabsf(e.uz) < FLT_EPSILON)) in = sglBarycentric(e, xy[2 * i], xy[2 * i + 1], b0, b1, b2);
+  bcOut[3 * i] = b0; bcOut[3 * i + 1] = b1; bcOut[3 * i + 2] = b2;
+  insideOut[i] = in ? 1 : 0;
+  zwOut[2 * i] = sglInterpZ(p, 2, b0, b1, b2);
+  zwOut[2 * i + 1] = sglInterpZ(p, 3, b0, b1, b2);
+}
+
+__global__ void sglKatSampleKernel(const SglTexObj *textures, int tex, int filter, int wrap, uint32_t border, const float *coords,
+                                   const float *lod, int n, uint32_t *out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  SglSampler s;
+  s.tex = &textures[tex];
+  s.filter = filter;
+  s.wrap = wrap;
+  s.border = border;
+  float l = lod ? lod[i] : 0.f;
+  if (s.tex->layers == 6) {
+    int face;
+    float u, v;
+    sglCubeFace(coords[3 * i], coords[3 * i + 1], coords[3 * i + 2], face, u, v);
+    out[i] = sglTextureImpl(s, face, u, v, l, 0, 0);
+  } else {
+    out[i] = sglTextureImpl(s, 0, coords[2 * i], coords[2 * i + 1], l, 0, 0);
+  }
+}
+
+__global__ void sglKatBlendKernel(SglRenderStates rs, const float *src, const float *dst, int n, float *out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  V4 s = v4(src[4 * i], src[4 * i + 1], src[4 * i + 2], src[4 * i + 3]);
+  // destination is given as floats in [0,1]; the pipeline reads it back from RGBA8
+  uint32_t dp = sglPackColor(v4(dst[4 * i], dst[4 * i + 1], dst[4 * i + 2], dst[4 * i + 3]));
+  V4 r = sglBlend(rs, s, dp);
+  out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+}
+
+__global__ void sglKatDepthKernel(int func, const float *a, const float *b, int n, int *out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = sglDepthTest(a[i], b[i], func) ? 1 : 0;
+}
+#endif  // SGL_RASTER_ONLY

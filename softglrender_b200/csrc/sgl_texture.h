@@ -1,0 +1,234 @@
+// Texturing: image layouts, wrap modes, nearest / bilinear / mip filtering and cube-face selection,
+// reading Linear, Tiled(4x4) and Morton(32x32) storage directly.  Restates, for the device:
+//   Buffer/TiledBuffer/MortonBuffer::convertIndex      src/Base/Buffer.h:31-33,151-158,185-202
+//   BaseSampler::textureImpl                           src/Render/Software/SamplerSoft.h:118-168
+//   BaseSampler::pixelWithWrapMode (incl. the CoordMod macro precedence quirk, :14) :171-213
+//   sampleNearest / sampleBilinear / samplePixelBilinear                             :216-266
+//   BaseSamplerCube::convertXYZ2UV                                                    :312-373
+// Texel arithmetic is 8-bit truncating exactly like glm::mix on u8vec4 in the oracle binary:
+//   mix(x, y, a) = u8( fma(float(y), a, rn(float(x) * (1 - a))) )     (objdump of samplePixelBilinear)
+#pragma once
+#include "sgl_math.h"
+#include "sgl_types.h"
+
+#if defined(__CUDA_ARCH__)
+#define SGL_LDG(p) __ldg(p)
+#else
+#define SGL_LDG(p) (*(p))
+#endif
+
+SGL_HD uint32_t sglMorton2(uint32_t x, uint32_t y) {   // MortonBuffer::encode16_morton2, x in even bits
+  uint32_t res = x | (y << 16);
+  res = (res | (res << 4)) & 0x0f0f0f0fu;
+  res = (res | (res << 2)) & 0x33333333u;
+  res = (res | (res << 1)) & 0x55555555u;
+  return (res | (res >> 15)) & 0xffffu;
+}
+
+SGL_HD size_t sglTexelIndex(int layout, int w, int x, int y) {
+  if (layout == SGL_LAYOUT_LINEAR) return (size_t) x + (size_t) y * (size_t) w;
+  if (layout == SGL_LAYOUT_TILED) {
+    int tw = (w + 3) >> 2;
+    return (((size_t) (y >> 2) * tw + (x >> 2)) << 4) + ((y & 3) << 2) + (x & 3);
+  }
+  int tw = (w + 31) >> 5;
+  return (((size_t) (y >> 5) * tw + (x >> 5)) << 10) + sglMorton2(x & 31, y & 31);
+}
+
+SGL_HD size_t sglLevelTexels(int layout, int w, int h) {   // innerWidth * innerHeight (Buffer.h:43-48,143-148,174-179)
+  if (layout == SGL_LAYOUT_LINEAR) return (size_t) w * h;
+  int ts = layout == SGL_LAYOUT_TILED ? 4 : 32;
+  return (size_t) ((w + ts - 1) / ts * ts) * (size_t) ((h + ts - 1) / ts * ts);
+}
+
+SGL_HD int sglLevelDim(int d, int level) { int v = d >> level; return v > 1 ? v : 1; }
+
+struct SglSampler {        // BaseSampler state after Sampler2DSoft/SamplerCubeSoft::setTexture (SamplerSoft.h:388-394,428-436)
+  const SglTexObj *tex;
+  int filter, wrap;
+  uint32_t border;
+};
+
+// pixelWithWrapMode: returns false when the border colour applies
+SGL_HD bool sglWrapCoord(int &x, int &y, int w, int h, int wrap) {
+  switch (wrap) {
+    case SGL_WRAP_REPEAT:
+      // #define CoordMod(i, n) ((i) & ((n) - 1) + (n)) & ((n) - 1)  ==  i & (2n-1) & (n-1)
+      x = (x & ((w - 1) + w)) & (w - 1);
+      y = (y & ((h - 1) + h)) & (h - 1);
+      break;
+    case SGL_WRAP_MIRRORED_REPEAT:
+      x = (x & ((2 * w - 1) + 2 * w)) & (2 * w - 1);
+      y = (y & ((2 * h - 1) + 2 * h)) & (2 * h - 1);
+      x -= w;
+      y -= h;
+      x = x >= 0 ? x : (-1 - x);
+      y = y >= 0 ? y : (-1 - y);
+      x = w - 1 - x;
+      y = h - 1 - y;
+      break;
+    case SGL_WRAP_CLAMP_TO_EDGE:
+      if (x < 0) x = 0;
+      if (y < 0) y = 0;
+      if (x >= w) x = w - 1;
+      if (y >= h) y = h - 1;
+      break;
+    case SGL_WRAP_CLAMP_TO_BORDER:
+      if (x < 0 || x >= w) return false;
+      if (y < 0 || y >= h) return false;
+      break;
+  }
+  return true;
+}
+
+// raw 32-bit texel (RGBA8 packed little-endian or float bits) of layer/level at integer coords with wrap
+SGL_HD uint32_t sglTexel(const SglSampler &s, int layer, int level, int x, int y) {
+  const SglTexObj *t = s.tex;
+  int w = sglLevelDim(t->width, level), h = sglLevelDim(t->height, level);
+  if (!sglWrapCoord(x, y, w, h, s.wrap)) return s.border;
+  if ((unsigned) x >= (unsigned) w || (unsigned) y >= (unsigned) h) return 0u;   // Buffer::get bounds check -> T(0)
+  const uint32_t *p = (const uint32_t *) (t->base + (size_t) layer * t->layerStride + t->levelOffset[level]);
+  return SGL_LDG(p + sglTexelIndex(t->layout, w, x, y));
+}
+
+SGL_HD uint32_t sglMixU8(uint32_t a, uint32_t b, float f, float omf) {
+  uint32_t r = 0;
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    float x = (float) ((a >> (8 * c)) & 0xffu), y = (float) ((b >> (8 * c)) & 0xffu);
+    float m = xfma(y, f, xmul(x, omf));
+    r |= ((uint32_t) (int) m & 0xffu) << (8 * c);
+  }
+  return r;
+}
+
+SGL_HD float sglMixF32(uint32_t a, uint32_t b, float f, float omf) {
+#if defined(__CUDA_ARCH__)
+  float x = __uint_as_float(a), y = __uint_as_float(b);
+#else
+  float x, y;
+  memcpy(&x, &a, 4);
+  memcpy(&y, &b, 4);
+#endif
+  return xfma(y, f, xmul(x, omf));
+}
+
+SGL_HD uint32_t sglFloatBits(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+#endif
+}
+SGL_HD float sglBitsFloat(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+
+SGL_HD uint32_t sglMixTexel(int format, uint32_t a, uint32_t b, float f) {
+  float omf = xsub(1.0f, f);
+  if (format == SGL_FMT_RGBA8) return sglMixU8(a, b, f, omf);
+  return sglFloatBits(sglMixF32(a, b, f, omf));
+}
+
+// samplePixelBilinear: uv in texel units of the level
+SGL_HD uint32_t sglPixelBilinear(const SglSampler &s, int layer, int level, float u, float v) {
+  float tu = xsub(u, 0.5f), tv = xsub(v, 0.5f);
+  float fu = floorf(tu), fv = floorf(tv);
+  int x = (int) fu, y = (int) fv;
+  uint32_t s1 = sglTexel(s, layer, level, x, y);
+  uint32_t s2 = sglTexel(s, layer, level, x + 1, y);
+  uint32_t s3 = sglTexel(s, layer, level, x, y + 1);
+  uint32_t s4 = sglTexel(s, layer, level, x + 1, y + 1);
+  float fx = xsub(tu, fu), fy = xsub(tv, fv);     // glm::fract(x) = x - floor(x)
+  int fmt = s.tex->format;
+  return sglMixTexel(fmt, sglMixTexel(fmt, s1, s2, fx), sglMixTexel(fmt, s3, s4, fx), fy);
+}
+
+SGL_HD uint32_t sglSampleNearest(const SglSampler &s, int layer, int level, float u, float v, int ox, int oy) {
+  const SglTexObj *t = s.tex;
+  float w = (float) sglLevelDim(t->width, level), h = (float) sglLevelDim(t->height, level);
+  int x = (int) floorf(xmul(u, w)) + ox;
+  int y = (int) floorf(xmul(v, h)) + oy;
+  return sglTexel(s, layer, level, x, y);
+}
+
+SGL_HD uint32_t sglSampleBilinear(const SglSampler &s, int layer, int level, float u, float v, int ox, int oy) {
+  const SglTexObj *t = s.tex;
+  float w = (float) sglLevelDim(t->width, level), h = (float) sglLevelDim(t->height, level);
+  float tu = xadd(xmul(u, w), (float) ox);
+  float tv = xadd(xmul(v, h), (float) oy);
+  return sglPixelBilinear(s, layer, level, tu, tv);
+}
+
+// BaseSampler::textureImpl
+SGL_HDN uint32_t sglTextureImpl(const SglSampler &s, int layer, float u, float v, float lod, int ox, int oy) {
+  const SglTexObj *t = s.tex;
+  if (t == nullptr || t->base == nullptr) return 0u;
+  int f = s.filter;
+  if (f == SGL_FILTER_NEAREST) return sglSampleNearest(s, layer, 0, u, v, ox, oy);
+  if (f == SGL_FILTER_LINEAR) return sglSampleBilinear(s, layer, 0, u, v, ox, oy);
+  int maxLevel = t->levels - 1;
+  if (f == SGL_FILTER_NEAREST_MIPMAP_NEAREST || f == SGL_FILTER_LINEAR_MIPMAP_NEAREST) {
+    int level = (int) ceilf(xadd(lod, 0.5f)) - 1;
+    level = level < 0 ? 0 : (level > maxLevel ? maxLevel : level);
+    if (f == SGL_FILTER_NEAREST_MIPMAP_NEAREST) return sglSampleNearest(s, layer, level, u, v, ox, oy);
+    return sglSampleBilinear(s, layer, level, u, v, ox, oy);
+  }
+  int hi = (int) floorf(lod);
+  hi = hi < 0 ? 0 : (hi > maxLevel ? maxLevel : hi);
+  int lo = hi + 1;
+  lo = lo < 0 ? 0 : (lo > maxLevel ? maxLevel : lo);
+  bool nearest = f == SGL_FILTER_NEAREST_MIPMAP_LINEAR;
+  uint32_t thi = nearest ? sglSampleNearest(s, layer, hi, u, v, ox, oy) : sglSampleBilinear(s, layer, hi, u, v, ox, oy);
+  if (hi == lo) return thi;
+  uint32_t tlo = nearest ? sglSampleNearest(s, layer, lo, u, v, ox, oy) : sglSampleBilinear(s, layer, lo, u, v, ox, oy);
+  float fr = xsub(lod, floorf(lod));
+  return sglMixTexel(t->format, thi, tlo, fr);
+}
+
+// BaseSamplerCube::convertXYZ2UV -- an if-chain where later matches override earlier ones on ties
+SGL_HD void sglCubeFace(float x, float y, float z, int &index, float &u, float &v) {
+  float absX = fabsf(x), absY = fabsf(y), absZ = fabsf(z);
+  bool xp = x > 0, yp = y > 0, zp = z > 0;
+  float maxAxis = 0.f, uc = 0.f, vc = 0.f;
+  index = 0;
+  if (xp && absX >= absY && absX >= absZ) { maxAxis = absX; uc = -z; vc = y; index = 0; }
+  if (!xp && absX >= absY && absX >= absZ) { maxAxis = absX; uc = z; vc = y; index = 1; }
+  if (yp && absY >= absX && absY >= absZ) { maxAxis = absY; uc = x; vc = -z; index = 2; }
+  if (!yp && absY >= absX && absY >= absZ) { maxAxis = absY; uc = x; vc = z; index = 3; }
+  if (zp && absZ >= absX && absZ >= absY) { maxAxis = absZ; uc = x; vc = y; index = 4; }
+  if (!zp && absZ >= absX && absZ >= absY) { maxAxis = absZ; uc = -x; vc = y; index = 5; }
+  vc = -vc;
+  u = 0.5f * (uc / maxAxis + 1.0f);
+  v = 0.5f * (vc / maxAxis + 1.0f);
+}
+
+SGL_HD V4 sglUnpackRGBA(uint32_t p) {   // vec4(u8vec4) / 255.f   (ShaderSoft.h:80-111)
+  return v4((float) (p & 0xffu) / 255.f, (float) ((p >> 8) & 0xffu) / 255.f, (float) ((p >> 16) & 0xffu) / 255.f,
+            (float) (p >> 24) / 255.f);
+}
+
+SGL_HD V4 sglTexture2D(const SglSampler &s, V2 uv, float lod) {
+  return sglUnpackRGBA(sglTextureImpl(s, 0, uv.x, uv.y, lod, 0, 0));
+}
+SGL_HD V4 sglTexture2DOffset(const SglSampler &s, V2 uv, float lod, int ox, int oy) {
+  return sglUnpackRGBA(sglTextureImpl(s, 0, uv.x, uv.y, lod, ox, oy));
+}
+SGL_HD float sglTexture2DFloat(const SglSampler &s, V2 uv) {
+  return sglBitsFloat(sglTextureImpl(s, 0, uv.x, uv.y, 0.f, 0, 0));
+}
+SGL_HD V4 sglTextureCube(const SglSampler &s, V3 dir, float lod) {
+  int face;
+  float u, v;
+  sglCubeFace(dir.x, dir.y, dir.z, face, u, v);
+  if (s.tex == nullptr || face >= s.tex->layers) return v4(0, 0, 0, 0);
+  return sglUnpackRGBA(sglTextureImpl(s, face, u, v, lod, 0, 0));
+}

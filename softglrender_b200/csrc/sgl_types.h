@@ -1,0 +1,125 @@
+// Device-visible PODs shared by the kernels and the C-ABI implementation.
+#pragma once
+#include <stdint.h>
+#include "../../include/sglcuda.h"
+
+#define SGL_TILE 16                 // screen tile = SGL_TILE x SGL_TILE pixels = one CTA of 256 threads
+#define SGL_TILE_THREADS (SGL_TILE * SGL_TILE)
+#define SGL_MAX_LEVELS 16
+#define SGL_OWNER_NONE 0xFFFFFFFFu
+#define SGL_BIG_PRIM_TILES 64       // primitives touching more tiles than this go to the pass-wide "big" list
+#define SGL_RASTER_BLOCK 32         // RendererSoft::rasterBlockSize_ (RendererSoft.h:128)
+
+// texture / attachment descriptor (TextureSoft<T> + ImageBufferSoft<T>, TextureSoft.h:20-255)
+struct SglTexObj {
+  uint8_t *base;                           // layers x levels, each level in `layout`
+  uint8_t *resolve;                        // resolved RGBA8 (the reference's `buffer` next to `bufferMs4x`) or null
+  unsigned long long levelOffset[SGL_MAX_LEVELS];  // bytes from the start of a layer
+  unsigned long long layerStride;          // bytes
+  int32_t width, height, levels, layers, format, samples, layout, pad;
+};
+
+// primitive kinds after assembly / polygon-mode expansion
+enum { SGL_PK_TRIANGLE = 0, SGL_PK_LINE = 1, SGL_PK_POINT = 2 };
+
+// flags of SglPrim
+#define SGL_PF_KIND_MASK 0x3u
+#define SGL_PF_FRONT (1u << 2)
+#define SGL_PF_IRREGULAR (1u << 3)   // block starts not contiguous (float rounding in RendererSoft.cpp:756-757): exact slow path
+#define SGL_PF_DEPTH_TEST (1u << 4)
+#define SGL_PF_DEPTH_MASK (1u << 5)
+#define SGL_PF_BLEND (1u << 6)
+#define SGL_PF_DEPTH_FUNC_SHIFT 7    // 3 bits
+#define SGL_PF_VALID (1u << 10)
+#define SGL_PF_STEEP (1u << 11)      // line: x/y swapped (RendererSoft.cpp:675-679)
+#define SGL_PF_SWAPPED (1u << 12)    // line: endpoints swapped (RendererSoft.cpp:683-689)
+
+// 64-byte primitive record, written by the setup kernel, read by the tile rasteriser
+struct __attribute__((aligned(16))) SglPrim {
+  // triangle: screen-space fragPos of the 3 vertices (x, y, z, 1/w)      (VertexHolder::fragPos, RendererInternal.h:39)
+  // line:     v[0] = (x0, y0, x1, y1) as int bits after steep/order swaps, v[1] = (z0, z1, w0, w1), v[2].x = lineWidth
+  // point:    v[0] = fragPos, v[1].x = pointSize
+  float v[3][4];
+  int16_t bx0, by0, bx1, by1;   // visited pixel range, inclusive (bbox + quad anchoring, RendererSoft.cpp:724-763)
+  uint32_t flags;
+  uint32_t draw;                // index into the pass' draw table
+};
+
+// vertex indices of a primitive (for varying interpolation at shading time)
+struct SglPrimVerts {
+  uint32_t i0, i1, i2, pad;
+};
+
+struct SglSamplerSlot {
+  int32_t tex;       // index into the device texture table, -1 = unbound
+  int32_t filter;
+  int32_t wrap;
+  uint32_t border;   // RGBA8 packed, or float bits for FLOAT32 textures
+};
+
+// per-draw record in device memory
+struct __attribute__((aligned(16))) SglDrawRec {
+  uint8_t uniforms[SGL_MAX_UNIFORM_BYTES];
+  SglSamplerSlot samplers[SGL_MAX_SAMPLER_SLOTS];
+  SglRenderStates rs;
+  int32_t shader;
+  uint32_t defines;
+  float vpX, vpY, vpW, vpH;               // Viewport (RendererInternal.h:14-28)
+  // geometry in
+  const float *vertexIn;                  // 16 floats per vertex
+  const int32_t *indices;
+  int32_t vertexCount, indexCount;
+  // vertex stage out (capacity = vertexCap, first vertexCount are the VAO vertices, rest clip-generated)
+  float *clipPos;                         // float4
+  float *fragPos;                         // float4
+  int32_t *clipMask;
+  float *vertexOut;                       // 16 floats per vertex: attributes of clip-generated vertices (for re-clipping)
+  float *varyings;                        // varyingStride floats per vertex
+  int32_t varyingStride, varyingCount;
+  int32_t vertexCap;
+  int32_t *vertexCounter;                 // next free vertex slot (starts at vertexCount)
+  // primitives
+  int32_t inputPrims;                     // points / lines / triangles assembled from the index buffer
+  int32_t slotsPerPrim;                   // 1, or 3 for polygon-mode LINE/POINT
+  int32_t primBase;                       // first slot in the pass' primitive arrays
+  int32_t appendBase, appendCap;          // fan triangles produced by clipping: slots [appendBase, appendBase+appendCap)
+  int32_t *appendCounter;
+  int32_t keyBase;                        // pass-global order key of slot 0
+  int32_t hasColor;
+  float pointSize;
+  int32_t pad[3];
+};
+
+// pass-level parameters
+struct SglPassParams {
+  // attachments
+  uint8_t *colorBase;       // RGBA8 [y][x][sample] of the attached layer/level, or null
+  float *depthBase;         // float [y][x][sample], or null
+  uint8_t *resolveBase;     // resolved colour (MS only), or null
+  int32_t fbW, fbH, samples;
+  int32_t clearColorFlag, clearDepthFlag;
+  uint32_t clearColor;      // RGBA8 packed (RendererSoft.cpp:72-75)
+  float clearDepth;
+  // tiles
+  int32_t tilesX, tilesY;
+  const uint8_t *tileOwner; // null = own all
+  int32_t rank;
+  // work
+  const SglDrawRec *draws;
+  int32_t drawCount;
+  const SglPrim *prims;
+  const SglPrimVerts *primVerts;
+  const uint32_t *primKeys;     // order key per primitive slot
+  int32_t primSlots;            // total slots in this pass
+  // bins
+  uint32_t *tileCount;          // [tiles]
+  uint32_t *tileOffset;         // [tiles+1]
+  uint32_t *tileCursor;         // [tiles]
+  uint32_t *binSlots;           // primitive slots per tile (unordered)
+  uint32_t binCapacity;
+  uint32_t *bigList;            // slots of big primitives
+  uint32_t *bigCount;
+  uint32_t bigCapacity;
+  const SglTexObj *textures;
+  unsigned long long *counters; // device-side SglCounters mirror
+};

@@ -1,0 +1,855 @@
+// libsglcuda.so -- C ABI (include/sglcuda.h) over the sm_100a kernels.
+// Host-side responsibilities: resource tables (buffers, textures), recording the draws of a render pass with
+// snapshots of uniforms/sampler bindings/states, laying out the pass' transient arena in HBM, and launching
+// the five kernels of sgl_kernels.cuh at sgl_pass_end (tile-based deferred execution, the model the reference's
+// own Vulkan backend uses behind the same API -- Render/Vulkan/RendererVulkan.cpp:73-205).
+#include "sgl_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// tile rasteriser instantiations live in their own translation units (sgl_raster_ns{1,4}.cu)
+extern "C" int sglLaunchRaster1(const SglPassParams *P, int nTiles, void *stream);
+extern "C" int sglLaunchRaster4(const SglPassParams *P, int nTiles, void *stream);
+
+namespace {
+
+struct BufferRec {
+  void *d = nullptr;
+  size_t bytes = 0;
+};
+
+struct TextureRec {
+  bool alive = false;
+  SglTextureDesc desc{};
+  SglTexObj obj{};
+  size_t bytes = 0;
+};
+
+struct Staging {
+  void *host = nullptr;
+  size_t cap = 0;
+  cudaEvent_t done = nullptr;
+  bool pending = false;
+};
+
+struct Ctx {
+  bool ready = false;
+  int device = 0, rank = 0, world = 1;
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+  std::vector<BufferRec> buffers{1};
+  std::vector<TextureRec> textures{1};
+  SglTexObj *dTextures = nullptr;
+  int dTexCap = 0;
+  // pass
+  bool inPass = false;
+  int colorTex = 0, colorLayer = 0, colorLevel = 0, depthTex = 0;
+  int clearColorFlag = 0, clearDepthFlag = 0;
+  float clearColor[4] = {0, 0, 0, 0};
+  float clearDepth = 1.f;
+  float vpX = 0, vpY = 0, vpW = 0, vpH = 0;
+  std::vector<SglDrawRec> draws;
+  // arena
+  uint8_t *arena = nullptr;
+  size_t arenaCap = 0;
+  Staging staging[4];
+  int stagingNext = 0;
+  // multi-GPU
+  uint8_t *dTileOwner = nullptr;
+  int ownerTilesX = 0, ownerTilesY = 0;
+  // counters
+  unsigned long long *dCounters = nullptr;
+  unsigned long long hostLaunches = 0, hostPasses = 0, hostDraws = 0;
+  cudaEvent_t evBegin = nullptr, evEnd = nullptr;
+  std::string err;
+};
+
+Ctx g;
+
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g.err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) return fail(SGL_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define NEED_CTX() \
+  if (!g.ready) return fail(SGL_ERR_STATE, "sgl_init has not been called (or failed)")
+
+size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int levelCount(const SglTextureDesc &d) {
+  if (!d.use_mipmaps) return 1;
+  int m = std::max(d.width, d.height), n = 0;
+  while ((1 << (n + 1)) <= m) n++;          // floor(log2(max(w,h))) + 1 levels (SamplerSoft.h:98)
+  return n + 1;
+}
+
+int uploadTexObj(int handle) {
+  if (handle >= g.dTexCap) {
+    int ncap = std::max(64, g.dTexCap * 2);
+    while (ncap <= handle) ncap *= 2;
+    SglTexObj *n = nullptr;
+    CU(cudaMalloc(&n, sizeof(SglTexObj) * ncap));
+    CU(cudaMemset(n, 0, sizeof(SglTexObj) * ncap));
+    if (g.dTextures) {
+      CU(cudaStreamSynchronize(g.stream));
+      CU(cudaMemcpy(n, g.dTextures, sizeof(SglTexObj) * g.dTexCap, cudaMemcpyDeviceToDevice));
+      CU(cudaFree(g.dTextures));
+    }
+    g.dTextures = n;
+    g.dTexCap = ncap;
+  }
+  CU(cudaMemcpyAsync(g.dTextures + handle, &g.textures[handle].obj, sizeof(SglTexObj), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaStreamSynchronize(g.stream));   // obj lives in a std::vector that may move
+  return SGL_OK;
+}
+
+TextureRec *tex(int h) {
+  if (h <= 0 || h >= (int) g.textures.size() || !g.textures[h].alive) return nullptr;
+  return &g.textures[h];
+}
+
+uint8_t *levelPtr(const TextureRec &t, int layer, int level) {
+  return t.obj.base + (size_t) layer * t.obj.layerStride + t.obj.levelOffset[level];
+}
+
+int ensureArena(size_t bytes) {
+  if (bytes <= g.arenaCap) return SGL_OK;
+  CU(cudaStreamSynchronize(g.stream));
+  if (g.arena) CU(cudaFree(g.arena));
+  g.arena = nullptr;
+  size_t ncap = alignUp(bytes + bytes / 4, 1 << 20);
+  cudaError_t e = cudaMalloc(&g.arena, ncap);
+  if (e != cudaSuccess) {
+    g.arenaCap = 0;
+    return fail(SGL_ERR_OOM, "pass arena of %zu bytes: %s", ncap, cudaGetErrorString(e));
+  }
+  g.arenaCap = ncap;
+  return SGL_OK;
+}
+
+int stagingAcquire(size_t bytes, Staging **out) {
+  Staging &s = g.staging[g.stagingNext];
+  g.stagingNext = (g.stagingNext + 1) % 4;
+  if (s.pending) {
+    CU(cudaEventSynchronize(s.done));
+    s.pending = false;
+  }
+  if (s.cap < bytes) {
+    if (s.host) CU(cudaFreeHost(s.host));
+    s.cap = alignUp(bytes * 2, 1 << 16);
+    CU(cudaMallocHost(&s.host, s.cap));
+  }
+  if (!s.done) CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  *out = &s;
+  return SGL_OK;
+}
+
+struct ShaderMeta {
+  const char *blocks[4];
+  int blockOffsets[4];
+  const char *samplers[8];
+  const char *defines[8];
+};
+
+const ShaderMeta *shaderMeta(int shader) {
+  // ShaderSoft::getUniformsDesc / getDefines of each program (e.g. PbrSoft.h:77-103, BlinnPhongSoft.h:71-96)
+  static const ShaderMeta basic = {{"UniformsModel", "UniformsMaterial"}, {0, 256}, {nullptr}, {nullptr}};
+  static const ShaderMeta blinn = {{"UniformsModel", "UniformsScene", "UniformsMaterial"}, {0, 256, 320},
+                                   {"u_albedoMap", "u_normalMap", "u_emissiveMap", "u_aoMap", "u_shadowMap"},
+                                   {"ALBEDO_MAP", "NORMAL_MAP", "EMISSIVE_MAP", "AO_MAP"}};
+  static const ShaderMeta pbr = {{"UniformsModel", "UniformsScene", "UniformsMaterial"}, {0, 256, 320},
+                                 {"u_albedoMap", "u_normalMap", "u_emissiveMap", "u_aoMap", "u_metalRoughnessMap",
+                                  "u_irradianceMap", "u_prefilterMap"},
+                                 {"ALBEDO_MAP", "NORMAL_MAP", "EMISSIVE_MAP", "AO_MAP", "METALROUGHNESS_MAP"}};
+  static const ShaderMeta sky = {{"UniformsModel"}, {0}, {"u_equirectangularMap", "u_cubeMap"}, {"EQUIRECTANGULAR_MAP"}};
+  static const ShaderMeta irr = {{"UniformsModel"}, {0}, {"u_cubeMap"}, {nullptr}};
+  static const ShaderMeta pre = {{"UniformsModel", "UniformsPrefilter"}, {0, 256}, {"u_cubeMap"}, {nullptr}};
+  static const ShaderMeta fxaa = {{"UniformsQuadFilter"}, {0}, {"u_screenTexture"}, {nullptr}};
+  switch (shader) {
+    case SGL_SHADER_BASIC: return &basic;
+    case SGL_SHADER_BLINNPHONG: return &blinn;
+    case SGL_SHADER_PBR: return &pbr;
+    case SGL_SHADER_SKYBOX: return &sky;
+    case SGL_SHADER_IBL_IRRADIANCE: return &irr;
+    case SGL_SHADER_IBL_PREFILTER: return &pre;
+    case SGL_SHADER_FXAA: return &fxaa;
+  }
+  return nullptr;
+}
+
+template<typename... Args>
+int launch(void (*kernel)(Args...), dim3 grid, dim3 block, Args... args) {
+  kernel<<<grid, block, 0, g.stream>>>(args...);
+  g.hostLaunches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SGL_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return SGL_OK;
+}
+
+}  // namespace
+
+namespace {
+template<typename T>
+struct DevTmp {
+  T *p = nullptr;
+  ~DevTmp() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
+};
+}  // namespace
+
+extern "C" {
+
+const char *sgl_last_error(void) { return g.err.c_str(); }
+
+int sgl_init(int device_ordinal, int rank, int world) {
+  if (g.ready) return SGL_OK;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(SGL_ERR_NO_DEVICE, "no CUDA device (%s); RendererCUDA has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device_ordinal < 0 || device_ordinal >= n) return fail(SGL_ERR_INVALID, "device ordinal %d out of range", device_ordinal);
+  CU(cudaSetDevice(device_ordinal));
+  g.device = device_ordinal;
+  g.rank = rank;
+  g.world = world < 1 ? 1 : world;
+  CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  g.ownStream = true;
+  CU(cudaMalloc(&g.dCounters, 8 * sizeof(unsigned long long)));
+  CU(cudaMemset(g.dCounters, 0, 8 * sizeof(unsigned long long)));
+  CU(cudaEventCreate(&g.evBegin));
+  CU(cudaEventCreate(&g.evEnd));
+  g.ready = true;
+  g.err.clear();
+  return SGL_OK;
+}
+
+int sgl_shutdown(void) {
+  if (!g.ready) return SGL_OK;
+  cudaStreamSynchronize(g.stream);
+  for (auto &b : g.buffers)
+    if (b.d) cudaFree(b.d);
+  for (auto &t : g.textures) {
+    if (t.alive && t.obj.base) cudaFree(t.obj.base);
+    if (t.alive && t.obj.resolve) cudaFree(t.obj.resolve);
+  }
+  if (g.dTextures) cudaFree(g.dTextures);
+  if (g.arena) cudaFree(g.arena);
+  if (g.dTileOwner) cudaFree(g.dTileOwner);
+  if (g.dCounters) cudaFree(g.dCounters);
+  for (auto &s : g.staging) {
+    if (s.host) cudaFreeHost(s.host);
+    if (s.done) cudaEventDestroy(s.done);
+  }
+  if (g.evBegin) cudaEventDestroy(g.evBegin);
+  if (g.evEnd) cudaEventDestroy(g.evEnd);
+  if (g.ownStream && g.stream) cudaStreamDestroy(g.stream);
+  g = Ctx();
+  return SGL_OK;
+}
+
+int sgl_set_stream(void *cuda_stream) {
+  NEED_CTX();
+  CU(cudaStreamSynchronize(g.stream));
+  if (g.ownStream && g.stream) cudaStreamDestroy(g.stream);
+  if (cuda_stream) {
+    g.stream = (cudaStream_t) cuda_stream;
+    g.ownStream = false;
+  } else {
+    CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    g.ownStream = true;
+  }
+  return SGL_OK;
+}
+
+int sgl_wait_idle(void) {
+  NEED_CTX();
+  CU(cudaStreamSynchronize(g.stream));
+  return SGL_OK;
+}
+
+int sgl_get_counters(SglCounters *out) {
+  NEED_CTX();
+  unsigned long long c[8];
+  CU(cudaStreamSynchronize(g.stream));
+  CU(cudaMemcpy(c, g.dCounters, sizeof(c), cudaMemcpyDeviceToHost));
+  out->passes = g.hostPasses;
+  out->draws = g.hostDraws;
+  out->primitives_in = c[2];
+  out->primitives_binned = c[3];
+  out->fragments_shaded = c[4];
+  out->samples_written = c[5];
+  out->kernel_launches = g.hostLaunches;
+  out->clip_overflow = c[7];
+  return SGL_OK;
+}
+
+int sgl_reset_counters(void) {
+  NEED_CTX();
+  CU(cudaStreamSynchronize(g.stream));
+  CU(cudaMemset(g.dCounters, 0, 8 * sizeof(unsigned long long)));
+  g.hostLaunches = g.hostPasses = g.hostDraws = 0;
+  return SGL_OK;
+}
+
+int sgl_timer_begin(void) {
+  NEED_CTX();
+  CU(cudaEventRecord(g.evBegin, g.stream));
+  return SGL_OK;
+}
+
+int sgl_timer_end(float *ms_out) {
+  NEED_CTX();
+  CU(cudaEventRecord(g.evEnd, g.stream));
+  CU(cudaEventSynchronize(g.evEnd));
+  CU(cudaEventElapsedTime(ms_out, g.evBegin, g.evEnd));
+  return SGL_OK;
+}
+
+// ---- reflection ---------------------------------------------------------------------------------------------
+int sgl_shader_uniform_offset(int shader, const char *name) {
+  const ShaderMeta *m = shaderMeta(shader);
+  if (!m || !name) return -1;
+  for (int i = 0; i < 4 && m->blocks[i]; i++)
+    if (!strcmp(m->blocks[i], name)) return m->blockOffsets[i];
+  return -1;
+}
+int sgl_shader_sampler_slot(int shader, const char *name) {
+  const ShaderMeta *m = shaderMeta(shader);
+  if (!m || !name) return -1;
+  for (int i = 0; i < 8 && m->samplers[i]; i++)
+    if (!strcmp(m->samplers[i], name)) return i;
+  return -1;
+}
+int sgl_shader_define_bit(int shader, const char *name) {
+  const ShaderMeta *m = shaderMeta(shader);
+  if (!m || !name) return -1;
+  for (int i = 0; i < 8 && m->defines[i]; i++)
+    if (!strcmp(m->defines[i], name)) return i;
+  return -1;
+}
+int sgl_shader_uniform_size(int shader) { return shaderMeta(shader) ? sglShaderInfo(shader).uniformBytes : -1; }
+int sgl_shader_varying_floats(int shader) { return shaderMeta(shader) ? sglShaderInfo(shader).varyingCount : -1; }
+
+// ---- buffers --------------------------------------------------------------------------------------------------
+int sgl_buffer_create(size_t bytes, const void *host_data, int *handle_out) {
+  NEED_CTX();
+  BufferRec b;
+  b.bytes = bytes;
+  CU(cudaMalloc(&b.d, std::max<size_t>(bytes, 16)));
+  if (host_data && bytes) CU(cudaMemcpyAsync(b.d, host_data, bytes, cudaMemcpyHostToDevice, g.stream));
+  CU(cudaStreamSynchronize(g.stream));   // caller's memory may go away (VertexArrayObjectSoft copies too, VertexSoft.h:16-27)
+  g.buffers.push_back(b);
+  *handle_out = (int) g.buffers.size() - 1;
+  return SGL_OK;
+}
+
+int sgl_buffer_upload(int handle, size_t offset, size_t bytes, const void *host_data) {
+  NEED_CTX();
+  if (handle <= 0 || handle >= (int) g.buffers.size() || !g.buffers[handle].d) return fail(SGL_ERR_INVALID, "bad buffer handle %d", handle);
+  BufferRec &b = g.buffers[handle];
+  if (offset > b.bytes) return SGL_OK;
+  bytes = std::min(bytes, b.bytes - offset);   // updateVertexData clamps to the buffer size (VertexSoft.h:29-31)
+  CU(cudaMemcpyAsync((uint8_t *) b.d + offset, host_data, bytes, cudaMemcpyHostToDevice, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  return SGL_OK;
+}
+
+int sgl_buffer_destroy(int handle) {
+  NEED_CTX();
+  if (handle <= 0 || handle >= (int) g.buffers.size()) return fail(SGL_ERR_INVALID, "bad buffer handle %d", handle);
+  CU(cudaStreamSynchronize(g.stream));
+  if (g.buffers[handle].d) CU(cudaFree(g.buffers[handle].d));
+  g.buffers[handle] = BufferRec();
+  return SGL_OK;
+}
+
+// ---- textures -------------------------------------------------------------------------------------------------
+int sgl_texture_create(const SglTextureDesc *desc, int *handle_out) {
+  NEED_CTX();
+  if (!desc || desc->width <= 0 || desc->height <= 0) return fail(SGL_ERR_INVALID, "texture size %dx%d", desc ? desc->width : 0, desc ? desc->height : 0);
+  if (desc->multi_sample && desc->layout != SGL_LAYOUT_LINEAR) return fail(SGL_ERR_INVALID, "multisample textures must be linear");
+  TextureRec t;
+  t.desc = *desc;
+  t.alive = true;
+  SglTexObj &o = t.obj;
+  o.width = desc->width;
+  o.height = desc->height;
+  o.levels = levelCount(*desc);
+  if (o.levels > SGL_MAX_LEVELS) return fail(SGL_ERR_INVALID, "too many mip levels");
+  o.layers = desc->type == SGL_TEX_CUBE ? 6 : 1;
+  o.format = desc->format;
+  o.samples = desc->multi_sample ? 4 : 1;
+  o.layout = desc->layout;
+  size_t offBytes = 0;
+  for (int l = 0; l < o.levels; l++) {
+    o.levelOffset[l] = offBytes;
+    size_t texels = sglLevelTexels(o.layout, sglLevelDim(o.width, l), sglLevelDim(o.height, l));
+    offBytes += alignUp(texels * 4 * o.samples, 256);
+  }
+  o.layerStride = offBytes;
+  t.bytes = offBytes * o.layers;
+  cudaError_t e = cudaMalloc(&o.base, t.bytes);
+  if (e != cudaSuccess) return fail(SGL_ERR_OOM, "texture of %zu bytes: %s", t.bytes, cudaGetErrorString(e));
+  CU(cudaMemsetAsync(o.base, 0, t.bytes, g.stream));
+  if (desc->multi_sample && desc->format == SGL_FMT_RGBA8) {
+    CU(cudaMalloc(&o.resolve, (size_t) o.width * o.height * 4));
+    CU(cudaMemsetAsync(o.resolve, 0, (size_t) o.width * o.height * 4, g.stream));
+  }
+  g.textures.push_back(t);
+  int h = (int) g.textures.size() - 1;
+  *handle_out = h;
+  return uploadTexObj(h);
+}
+
+int sgl_texture_destroy(int handle) {
+  NEED_CTX();
+  TextureRec *t = tex(handle);
+  if (!t) return fail(SGL_ERR_INVALID, "bad texture handle %d", handle);
+  CU(cudaStreamSynchronize(g.stream));
+  if (t->obj.base) CU(cudaFree(t->obj.base));
+  if (t->obj.resolve) CU(cudaFree(t->obj.resolve));
+  *t = TextureRec();
+  return SGL_OK;
+}
+
+int sgl_texture_level_size(int handle, int level, int *w_out, int *h_out) {
+  NEED_CTX();
+  TextureRec *t = tex(handle);
+  if (!t || level < 0 || level >= t->obj.levels) return fail(SGL_ERR_INVALID, "bad texture/level %d/%d", handle, level);
+  *w_out = sglLevelDim(t->obj.width, level);
+  *h_out = sglLevelDim(t->obj.height, level);
+  return SGL_OK;
+}
+
+int sgl_texture_upload(int handle, int layer, int level, const void *host_data) {
+  NEED_CTX();
+  TextureRec *t = tex(handle);
+  if (!t || layer < 0 || layer >= t->obj.layers || level < 0 || level >= t->obj.levels) return fail(SGL_ERR_INVALID, "bad texture upload target");
+  if (t->obj.samples != 1) return fail(SGL_ERR_INVALID, "setImageData not supported on multisample textures");   // TextureSoft.h:115-118
+  int w = sglLevelDim(t->obj.width, level), h = sglLevelDim(t->obj.height, level);
+  size_t bytes = (size_t) w * h * 4;
+  uint8_t *dst = levelPtr(*t, layer, level);
+  if (t->obj.layout == SGL_LAYOUT_LINEAR) {
+    CU(cudaMemcpyAsync(dst, host_data, bytes, cudaMemcpyHostToDevice, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    return SGL_OK;
+  }
+  void *tmp = nullptr;
+  CU(cudaMalloc(&tmp, bytes));
+  CU(cudaMemcpyAsync(tmp, host_data, bytes, cudaMemcpyHostToDevice, g.stream));
+  dim3 blk(16, 16), grd((w + 15) / 16, (h + 15) / 16);
+  int rc = launch(sglRelayoutKernel, grd, blk, (uint32_t *) dst, (const uint32_t *) tmp, w, h, t->obj.layout, 1);
+  CU(cudaStreamSynchronize(g.stream));
+  CU(cudaFree(tmp));
+  return rc;
+}
+
+int sgl_texture_gen_mips(int handle) {
+  NEED_CTX();
+  TextureRec *t = tex(handle);
+  if (!t) return fail(SGL_ERR_INVALID, "bad texture handle %d", handle);
+  for (int layer = 0; layer < t->obj.layers; layer++)
+    for (int level = 1; level < t->obj.levels; level++) {
+      int w = sglLevelDim(t->obj.width, level), h = sglLevelDim(t->obj.height, level);
+      dim3 blk(16, 16), grd((w + 15) / 16, (h + 15) / 16);
+      int rc = launch(sglMipKernel, grd, blk, t->obj, layer, level);
+      if (rc) return rc;
+    }
+  return SGL_OK;
+}
+
+int sgl_texture_device_ptr(int handle, int layer, int level, int kind, void **ptr_out, size_t *bytes_out) {
+  NEED_CTX();
+  TextureRec *t = tex(handle);
+  if (!t || layer < 0 || layer >= t->obj.layers || level < 0 || level >= t->obj.levels) return fail(SGL_ERR_INVALID, "bad texture/layer/level");
+  int w = sglLevelDim(t->obj.width, level), h = sglLevelDim(t->obj.height, level);
+  if (kind == 1) {
+    if (!t->obj.resolve) return fail(SGL_ERR_INVALID, "texture has no resolved colour buffer");
+    *ptr_out = t->obj.resolve;
+    *bytes_out = (size_t) w * h * 4;
+  } else {
+    *ptr_out = levelPtr(*t, layer, level);
+    *bytes_out = sglLevelTexels(t->obj.layout, w, h) * 4 * t->obj.samples;
+  }
+  return SGL_OK;
+}
+
+int sgl_texture_readback(int handle, int layer, int level, int kind, void *host_out, size_t bytes) {
+  NEED_CTX();
+  TextureRec *t = tex(handle);
+  if (!t || layer < 0 || layer >= t->obj.layers || level < 0 || level >= t->obj.levels) return fail(SGL_ERR_INVALID, "bad texture/layer/level");
+  int w = sglLevelDim(t->obj.width, level), h = sglLevelDim(t->obj.height, level);
+  CU(cudaStreamSynchronize(g.stream));
+  if (kind == 1) {
+    if (!t->obj.resolve) return fail(SGL_ERR_INVALID, "texture has no resolved colour buffer");
+    size_t need = (size_t) w * h * 4;
+    if (bytes < need) return fail(SGL_ERR_INVALID, "readback buffer too small");
+    CU(cudaMemcpy(host_out, t->obj.resolve, need, cudaMemcpyDeviceToHost));
+    return SGL_OK;
+  }
+  size_t need = (size_t) w * h * 4 * t->obj.samples;
+  if (bytes < need) return fail(SGL_ERR_INVALID, "readback buffer too small");
+  uint8_t *src = levelPtr(*t, layer, level);
+  if (t->obj.layout == SGL_LAYOUT_LINEAR) {
+    CU(cudaMemcpy(host_out, src, need, cudaMemcpyDeviceToHost));
+    return SGL_OK;
+  }
+  void *tmp = nullptr;
+  CU(cudaMalloc(&tmp, need));
+  dim3 blk(16, 16), grd((w + 15) / 16, (h + 15) / 16);
+  int rc = launch(sglRelayoutKernel, grd, blk, (uint32_t *) tmp, (const uint32_t *) src, w, h, t->obj.layout, 0);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(g.stream));
+  CU(cudaMemcpy(host_out, tmp, need, cudaMemcpyDeviceToHost));
+  CU(cudaFree(tmp));
+  return SGL_OK;
+}
+
+// ---- render pass ----------------------------------------------------------------------------------------------
+int sgl_pass_begin(int color_tex, int color_layer, int color_level, int depth_tex, int clear_color_flag,
+                   int clear_depth_flag, const float clear_color[4], float clear_depth) {
+  NEED_CTX();
+  if (g.inPass) return fail(SGL_ERR_STATE, "sgl_pass_begin inside a pass");
+  if (color_tex && !tex(color_tex)) return fail(SGL_ERR_INVALID, "bad colour attachment %d", color_tex);
+  if (depth_tex && !tex(depth_tex)) return fail(SGL_ERR_INVALID, "bad depth attachment %d", depth_tex);
+  if (!color_tex && !depth_tex) return fail(SGL_ERR_INVALID, "render pass without attachments");
+  if (color_tex) {
+    TextureRec *t = tex(color_tex);
+    if (t->obj.format != SGL_FMT_RGBA8 || t->obj.layout != SGL_LAYOUT_LINEAR) return fail(SGL_ERR_INVALID, "colour attachment must be linear RGBA8");
+    if (color_layer < 0 || color_layer >= t->obj.layers || color_level < 0 || color_level >= t->obj.levels)
+      return fail(SGL_ERR_INVALID, "colour attachment layer/level out of range");
+  }
+  if (depth_tex) {
+    TextureRec *t = tex(depth_tex);
+    if (t->obj.format != SGL_FMT_FLOAT32 || t->obj.layout != SGL_LAYOUT_LINEAR) return fail(SGL_ERR_INVALID, "depth attachment must be linear FLOAT32");
+  }
+  if (color_tex && depth_tex) {
+    TextureRec *c = tex(color_tex), *d = tex(depth_tex);
+    if (c->obj.samples != d->obj.samples) return fail(SGL_ERR_INVALID, "attachment sample counts differ");
+    if (sglLevelDim(c->obj.width, color_level) != d->obj.width || sglLevelDim(c->obj.height, color_level) != d->obj.height)
+      return fail(SGL_ERR_INVALID, "attachment sizes differ");
+  }
+  g.inPass = true;
+  g.colorTex = color_tex;
+  g.colorLayer = color_layer;
+  g.colorLevel = color_level;
+  g.depthTex = depth_tex;
+  g.clearColorFlag = clear_color_flag;
+  g.clearDepthFlag = clear_depth_flag;
+  if (clear_color) memcpy(g.clearColor, clear_color, 16);
+  g.clearDepth = clear_depth;
+  g.draws.clear();
+  return SGL_OK;
+}
+
+int sgl_set_viewport(int x, int y, int width, int height) {
+  NEED_CTX();
+  g.vpX = (float) x;
+  g.vpY = (float) y;
+  g.vpW = (float) width;
+  g.vpH = (float) height;
+  return SGL_OK;
+}
+
+int sgl_draw(const SglDraw *draw) {
+  NEED_CTX();
+  if (!g.inPass) return fail(SGL_ERR_STATE, "sgl_draw outside a render pass");
+  if (!draw || !shaderMeta(draw->shader)) return fail(SGL_ERR_INVALID, "unknown shader %d", draw ? draw->shader : -1);
+  if (draw->vertex_buffer <= 0 || draw->vertex_buffer >= (int) g.buffers.size() || !g.buffers[draw->vertex_buffer].d)
+    return fail(SGL_ERR_INVALID, "bad vertex buffer");
+  if (draw->index_buffer <= 0 || draw->index_buffer >= (int) g.buffers.size() || !g.buffers[draw->index_buffer].d)
+    return fail(SGL_ERR_INVALID, "bad index buffer");
+  if ((size_t) draw->vertex_count * SGL_VERTEX_STRIDE > g.buffers[draw->vertex_buffer].bytes ||
+      (size_t) draw->index_count * 4 > g.buffers[draw->index_buffer].bytes)
+    return fail(SGL_ERR_INVALID, "draw exceeds buffer size");
+  SglDrawRec r;
+  memset(&r, 0, sizeof(r));
+  size_t ub = std::min<size_t>(draw->uniform_bytes, SGL_MAX_UNIFORM_BYTES);
+  memcpy(r.uniforms, draw->uniforms, ub);
+  for (int s = 0; s < SGL_MAX_SAMPLER_SLOTS; s++) {
+    const SglSamplerBinding &b = draw->samplers[s];
+    TextureRec *t = b.texture ? tex(b.texture) : nullptr;
+    r.samplers[s].tex = t ? b.texture : -1;
+    r.samplers[s].filter = b.filter_min;
+    r.samplers[s].wrap = b.wrap;
+    // TextureSoft::getBorderColor (TextureSoft.h:158-164): float -> clamp(r), RGBA -> clamp(c*255)
+    float bc = b.border == SGL_BORDER_WHITE ? 1.f : 0.f;
+    if (t && t->obj.format == SGL_FMT_FLOAT32) memcpy(&r.samplers[s].border, &bc, 4);
+    else r.samplers[s].border = b.border == SGL_BORDER_WHITE ? 0xFFFFFFFFu : 0u;
+  }
+  r.rs = draw->states;
+  r.shader = draw->shader;
+  r.defines = draw->defines;
+  r.vpX = g.vpX; r.vpY = g.vpY; r.vpW = g.vpW; r.vpH = g.vpH;
+  r.vertexIn = (const float *) g.buffers[draw->vertex_buffer].d;
+  r.indices = (const int32_t *) g.buffers[draw->index_buffer].d;
+  r.vertexCount = draw->vertex_count;
+  r.indexCount = draw->index_count;
+  SglShaderInfo info = sglShaderInfo(draw->shader);
+  r.varyingStride = info.varyingStride;
+  r.varyingCount = info.varyingCount;
+  // gl_PointSize: only ShaderBasic::VS writes it (BasicSoft.h:68); other programs keep the builtin's 1.0 (ShaderSoft.h:30)
+  r.pointSize = 1.f;
+  if (draw->shader == SGL_SHADER_BASIC) memcpy(&r.pointSize, r.uniforms + 268, 4);
+  r.hasColor = g.colorTex != 0;
+  g.draws.push_back(r);
+  return SGL_OK;
+}
+
+int sgl_pass_end(void) {
+  NEED_CTX();
+  if (!g.inPass) return fail(SGL_ERR_STATE, "sgl_pass_end outside a pass");
+  g.inPass = false;
+  TextureRec *ct = g.colorTex ? tex(g.colorTex) : nullptr;
+  TextureRec *dt = g.depthTex ? tex(g.depthTex) : nullptr;
+  if ((g.colorTex && !ct) || (g.depthTex && !dt)) return fail(SGL_ERR_INVALID, "attachment destroyed during pass");
+  const int fbW = ct ? sglLevelDim(ct->obj.width, g.colorLevel) : dt->obj.width;
+  const int fbH = ct ? sglLevelDim(ct->obj.height, g.colorLevel) : dt->obj.height;
+  const int samples = ct ? ct->obj.samples : dt->obj.samples;
+  const int tilesX = (fbW + SGL_TILE - 1) / SGL_TILE, tilesY = (fbH + SGL_TILE - 1) / SGL_TILE;
+  const int nTiles = tilesX * tilesY;
+  const int nDraws = (int) g.draws.size();
+
+  // ---- arena layout
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = alignUp(off + bytes, 256); return o; };
+  size_t oDraws = take(sizeof(SglDrawRec) * std::max(nDraws, 1));
+  // zero-initialised region: per-draw counters, big count, tile counts, tile cursors
+  size_t oZero = off;
+  size_t oDrawCounters = take(sizeof(int32_t) * 2 * std::max(nDraws, 1));
+  size_t oBigCount = take(sizeof(uint32_t));
+  size_t oTileCount = take(sizeof(uint32_t) * nTiles);
+  size_t oTileCursor = take(sizeof(uint32_t) * nTiles);
+  size_t zeroBytes = off - oZero;
+  size_t oTileOffset = take(sizeof(uint32_t) * (nTiles + 1));
+  int primSlots = 0, keyBase = 0, maxVerts = 0, maxPrims = 0, maxSlots = 0;
+  std::vector<size_t> oClip(nDraws), oFrag(nDraws), oMask(nDraws), oVout(nDraws), oVary(nDraws);
+  for (int i = 0; i < nDraws; i++) {
+    SglDrawRec &r = g.draws[i];
+    const int pt = r.rs.primitive_type;
+    const int per = pt == SGL_PRIM_TRIANGLE ? 3 : (pt == SGL_PRIM_LINE ? 2 : 1);
+    r.inputPrims = r.indexCount / per;
+    const bool fill = pt == SGL_PRIM_TRIANGLE && r.rs.polygon_mode == SGL_POLY_FILL;
+    r.slotsPerPrim = (pt == SGL_PRIM_TRIANGLE && !fill) ? 3 : 1;
+    int extraVerts;
+    if (fill) extraVerts = (int) std::min<long long>(12LL * r.inputPrims, std::max<long long>(4096, 2LL * r.inputPrims));
+    else if (pt == SGL_PRIM_POINT) extraVerts = 0;
+    else extraVerts = (pt == SGL_PRIM_LINE ? 2 : 6) * r.inputPrims;
+    r.vertexCap = r.vertexCount + extraVerts;
+    r.appendCap = fill ? (int) std::min<long long>(6LL * r.inputPrims, std::max<long long>(1024, r.inputPrims)) : 0;
+    r.primBase = primSlots;
+    r.appendBase = primSlots + r.inputPrims * r.slotsPerPrim;
+    primSlots = r.appendBase + r.appendCap;
+    r.keyBase = keyBase;
+    keyBase += r.inputPrims * r.slotsPerPrim + (fill ? 6 * r.inputPrims : 0);
+    oClip[i] = take((size_t) r.vertexCap * 16);
+    oFrag[i] = take((size_t) r.vertexCap * 16);
+    oMask[i] = take((size_t) r.vertexCap * 4);
+    oVout[i] = take((size_t) std::max(extraVerts, 1) * 64);
+    oVary[i] = take((size_t) r.vertexCap * std::max(r.varyingStride, 1) * 4);
+    maxVerts = std::max(maxVerts, r.vertexCount);
+    maxPrims = std::max(maxPrims, r.inputPrims);
+    maxSlots = std::max(maxSlots, r.inputPrims * r.slotsPerPrim + r.appendCap);
+  }
+  if (primSlots >= (1 << 29)) return fail(SGL_ERR_OVERFLOW, "too many primitive slots in one pass (%d)", primSlots);
+  size_t oPrims = take(sizeof(SglPrim) * std::max(primSlots, 1));
+  size_t oPrimVerts = take(sizeof(SglPrimVerts) * std::max(primSlots, 1));
+  size_t oPrimKeys = take(sizeof(uint32_t) * std::max(primSlots, 1));
+  size_t oBigList = take(sizeof(uint32_t) * std::max(primSlots, 1));
+  size_t binCapacity = std::min<size_t>(std::max<size_t>((size_t) primSlots * 8, 1 << 20), (size_t) 1 << 29);
+  size_t oBins = take(sizeof(uint32_t) * binCapacity);
+  int rc = ensureArena(off);
+  if (rc) return rc;
+  uint8_t *A = g.arena;
+
+  for (int i = 0; i < nDraws; i++) {
+    SglDrawRec &r = g.draws[i];
+    r.clipPos = (float *) (A + oClip[i]);
+    r.fragPos = (float *) (A + oFrag[i]);
+    r.clipMask = (int32_t *) (A + oMask[i]);
+    r.vertexOut = (float *) (A + oVout[i]);
+    r.varyings = (float *) (A + oVary[i]);
+    r.vertexCounter = (int32_t *) (A + oDrawCounters) + 2 * i;
+    r.appendCounter = (int32_t *) (A + oDrawCounters) + 2 * i + 1;
+  }
+  CU(cudaMemsetAsync(A + oZero, 0, zeroBytes, g.stream));
+  if (nDraws) {
+    Staging *st = nullptr;
+    rc = stagingAcquire(sizeof(SglDrawRec) * nDraws, &st);
+    if (rc) return rc;
+    memcpy(st->host, g.draws.data(), sizeof(SglDrawRec) * nDraws);
+    CU(cudaMemcpyAsync(A + oDraws, st->host, sizeof(SglDrawRec) * nDraws, cudaMemcpyHostToDevice, g.stream));
+    CU(cudaEventRecord(st->done, g.stream));
+    st->pending = true;
+  }
+
+  SglPassParams P;
+  memset(&P, 0, sizeof(P));
+  P.colorBase = ct ? levelPtr(*ct, g.colorLayer, g.colorLevel) : nullptr;
+  P.depthBase = dt ? (float *) levelPtr(*dt, 0, 0) : nullptr;
+  P.resolveBase = (ct && samples > 1) ? ct->obj.resolve : nullptr;
+  P.fbW = fbW; P.fbH = fbH; P.samples = samples;
+  P.clearColorFlag = g.clearColorFlag;
+  P.clearDepthFlag = g.clearDepthFlag;
+  {  // RGBA(clear * 255) truncation (RendererSoft.cpp:72-75)
+    uint32_t c = 0;
+    for (int k = 0; k < 4; k++) c |= ((uint32_t) (uint8_t) (int) (g.clearColor[k] * 255.f)) << (8 * k);
+    P.clearColor = c;
+  }
+  P.clearDepth = g.clearDepth;
+  P.tilesX = tilesX; P.tilesY = tilesY;
+  P.tileOwner = (g.dTileOwner && g.ownerTilesX == tilesX && g.ownerTilesY == tilesY) ? g.dTileOwner : nullptr;
+  P.rank = g.rank;
+  P.draws = (const SglDrawRec *) (A + oDraws);
+  P.drawCount = nDraws;
+  P.prims = (const SglPrim *) (A + oPrims);
+  P.primVerts = (const SglPrimVerts *) (A + oPrimVerts);
+  P.primKeys = (const uint32_t *) (A + oPrimKeys);
+  P.primSlots = primSlots;
+  P.tileCount = (uint32_t *) (A + oTileCount);
+  P.tileOffset = (uint32_t *) (A + oTileOffset);
+  P.tileCursor = (uint32_t *) (A + oTileCursor);
+  P.binSlots = (uint32_t *) (A + oBins);
+  P.binCapacity = (uint32_t) binCapacity;
+  P.bigList = (uint32_t *) (A + oBigList);
+  P.bigCount = (uint32_t *) (A + oBigCount);
+  P.bigCapacity = (uint32_t) std::max(primSlots, 1);
+  P.textures = g.dTextures;
+  P.counters = g.dCounters;
+
+  if (nDraws) {
+    if (maxVerts > 0) {
+      rc = launch(sglVertexKernel, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws);
+      if (rc) return rc;
+    }
+    if (maxPrims > 0) {
+      SglSetupOut so = {(SglPrim *) (A + oPrims), (SglPrimVerts *) (A + oPrimVerts), (uint32_t *) (A + oPrimKeys)};
+      SglSetupShared ss;
+      ss.tileCount = P.tileCount; ss.bigList = P.bigList; ss.bigCount = P.bigCount; ss.bigCapacity = P.bigCapacity;
+      ss.counters = g.dCounters; ss.tilesX = tilesX; ss.tilesY = tilesY; ss.fbW = fbW; ss.fbH = fbH;
+      ss.tileOwner = P.tileOwner; ss.rank = g.rank;
+      rc = launch(sglSetupKernel, dim3((maxPrims + 127) / 128, nDraws), dim3(128), P.draws, so, ss, dt ? 1 : 0);
+      if (rc) return rc;
+    }
+  }
+  rc = launch(sglTileScanKernel, dim3(1), dim3(1024), (const uint32_t *) P.tileCount, P.tileOffset, nTiles, g.dCounters);
+  if (rc) return rc;
+  if (nDraws && maxSlots > 0) {
+    rc = launch(sglBinFillKernel, dim3((maxSlots + 255) / 256, nDraws), dim3(256), P);
+    if (rc) return rc;
+  }
+  {
+    int e = samples == 4 ? sglLaunchRaster4(&P, nTiles, (void *) g.stream) : sglLaunchRaster1(&P, nTiles, (void *) g.stream);
+    g.hostLaunches++;
+    if (e != 0) return fail(SGL_ERR_CUDA, "raster kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
+  }
+  g.hostPasses++;
+  g.hostDraws += nDraws;
+  g.draws.clear();
+  return SGL_OK;
+}
+
+// ---- multi-GPU --------------------------------------------------------------------------------------------------
+int sgl_tile_size(void) { return SGL_TILE; }
+
+int sgl_set_tile_owner_map(const uint8_t *owner, int tiles_x, int tiles_y) {
+  NEED_CTX();
+  CU(cudaStreamSynchronize(g.stream));
+  if (g.dTileOwner) CU(cudaFree(g.dTileOwner));
+  g.dTileOwner = nullptr;
+  g.ownerTilesX = g.ownerTilesY = 0;
+  if (!owner) return SGL_OK;
+  if (tiles_x <= 0 || tiles_y <= 0) return fail(SGL_ERR_INVALID, "bad tile map size");
+  CU(cudaMalloc(&g.dTileOwner, (size_t) tiles_x * tiles_y));
+  CU(cudaMemcpy(g.dTileOwner, owner, (size_t) tiles_x * tiles_y, cudaMemcpyHostToDevice));
+  g.ownerTilesX = tiles_x;
+  g.ownerTilesY = tiles_y;
+  return SGL_OK;
+}
+
+// ---- KATs -------------------------------------------------------------------------------------------------------
+
+int sgl_kat_barycentric(const float *tri_xyzw, const float *sample_xy, int n, float *bc_out, int *inside_out, float *zw_out) {
+  NEED_CTX();
+  DevTmp<float> dTri, dXy, dBc, dZw;
+  DevTmp<int> dIn;
+  CU(dTri.alloc(12)); CU(dXy.alloc(2 * n)); CU(dBc.alloc(3 * n)); CU(dZw.alloc(2 * n)); CU(dIn.alloc(n));
+  CU(cudaMemcpy(dTri.p, tri_xyzw, 48, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dXy.p, sample_xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice));
+  int rc = launch(sglKatBarycentricKernel, dim3((n + 127) / 128), dim3(128), (const float *) dTri.p, (const float *) dXy.p, n, dBc.p, dIn.p, dZw.p);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(g.stream));
+  CU(cudaMemcpy(bc_out, dBc.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(inside_out, dIn.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(zw_out, dZw.p, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost));
+  return SGL_OK;
+}
+
+int sgl_kat_sample(int texture, int filter_min, int wrap, int border, const float *coords, const float *lod, int n,
+                   uint32_t *out) {
+  NEED_CTX();
+  TextureRec *t = tex(texture);
+  if (!t) return fail(SGL_ERR_INVALID, "bad texture handle %d", texture);
+  int comps = t->obj.layers == 6 ? 3 : 2;
+  DevTmp<float> dC, dL;
+  DevTmp<uint32_t> dO;
+  CU(dC.alloc((size_t) comps * n)); CU(dL.alloc(n)); CU(dO.alloc(n));
+  CU(cudaMemcpy(dC.p, coords, sizeof(float) * comps * n, cudaMemcpyHostToDevice));
+  if (lod) CU(cudaMemcpy(dL.p, lod, sizeof(float) * n, cudaMemcpyHostToDevice));
+  uint32_t b;
+  float bf = border == SGL_BORDER_WHITE ? 1.f : 0.f;
+  if (t->obj.format == SGL_FMT_FLOAT32) memcpy(&b, &bf, 4);
+  else b = border == SGL_BORDER_WHITE ? 0xFFFFFFFFu : 0u;
+  int rc = launch(sglKatSampleKernel, dim3((n + 127) / 128), dim3(128), (const SglTexObj *) g.dTextures, texture, filter_min, wrap, b,
+                  (const float *) dC.p, lod ? (const float *) dL.p : (const float *) nullptr, n, dO.p);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(g.stream));
+  CU(cudaMemcpy(out, dO.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+  return SGL_OK;
+}
+
+int sgl_kat_blend(const SglRenderStates *states, const float *src_rgba, const float *dst_rgba, int n, float *out_rgba) {
+  NEED_CTX();
+  DevTmp<float> dS, dD, dO;
+  CU(dS.alloc(4 * n)); CU(dD.alloc(4 * n)); CU(dO.alloc(4 * n));
+  CU(cudaMemcpy(dS.p, src_rgba, sizeof(float) * 4 * n, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dD.p, dst_rgba, sizeof(float) * 4 * n, cudaMemcpyHostToDevice));
+  int rc = launch(sglKatBlendKernel, dim3((n + 127) / 128), dim3(128), *states, (const float *) dS.p, (const float *) dD.p, n, dO.p);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(g.stream));
+  CU(cudaMemcpy(out_rgba, dO.p, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost));
+  return SGL_OK;
+}
+
+int sgl_kat_depth(int func, const float *a, const float *b, int n, int *pass_out) {
+  NEED_CTX();
+  DevTmp<float> dA, dB;
+  DevTmp<int> dO;
+  CU(dA.alloc(n)); CU(dB.alloc(n)); CU(dO.alloc(n));
+  CU(cudaMemcpy(dA.p, a, sizeof(float) * n, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dB.p, b, sizeof(float) * n, cudaMemcpyHostToDevice));
+  int rc = launch(sglKatDepthKernel, dim3((n + 127) / 128), dim3(128), func, (const float *) dA.p, (const float *) dB.p, n, dO.p);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(g.stream));
+  CU(cudaMemcpy(pass_out, dO.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  return SGL_OK;
+}
+
+}  // extern "C"
