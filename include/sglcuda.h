@@ -112,6 +112,16 @@ int sgl_reset_counters(void);
 int sgl_timer_begin(void);
 int sgl_timer_end(float *ms_out);
 
+/* per-kernel device timing for bench.py's roofline block: while profiling is on every kernel launch is bracketed
+ * by CUDA events on the library's stream; sgl_get_kernel_times drains them (accumulated per kernel name). */
+typedef struct SglKernelTime {
+  char name[48];
+  uint64_t launches;
+  double total_ms;
+} SglKernelTime;
+int sgl_set_profiling(int on);
+int sgl_get_kernel_times(SglKernelTime *out, int capacity);   /* returns the number of entries written */
+
 /* ---- shader reflection (ShaderSoft::getUniformsDesc / getDefines, e.g. PbrSoft.h:77-103) -------------- */
 int sgl_shader_uniform_offset(int shader, const char *name);   /* byte offset or -1 */
 int sgl_shader_sampler_slot(int shader, const char *name);     /* slot or -1 */

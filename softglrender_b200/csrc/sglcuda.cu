@@ -193,12 +193,43 @@ const ShaderMeta *shaderMeta(int shader) {
   return nullptr;
 }
 
+struct ProfEvent {
+  const char *name;
+  cudaEvent_t a, b;
+};
+std::vector<ProfEvent> gProf;
+std::vector<cudaEvent_t> gProfPool;
+bool gProfiling = false;
+
+cudaEvent_t profEvent() {
+  cudaEvent_t e = nullptr;
+  if (!gProfPool.empty()) {
+    e = gProfPool.back();
+    gProfPool.pop_back();
+  } else {
+    cudaEventCreate(&e);
+  }
+  return e;
+}
+void profBegin(const char *name) {
+  if (!gProfiling) return;
+  ProfEvent p = {name, profEvent(), profEvent()};
+  cudaEventRecord(p.a, g.stream);
+  gProf.push_back(p);
+}
+void profEnd() {
+  if (!gProfiling) return;
+  cudaEventRecord(gProf.back().b, g.stream);
+}
+
 template<typename... Args>
-int launch(void (*kernel)(Args...), dim3 grid, dim3 block, Args... args) {
+int launch(const char *name, void (*kernel)(Args...), dim3 grid, dim3 block, Args... args) {
+  profBegin(name);
   kernel<<<grid, block, 0, g.stream>>>(args...);
+  profEnd();
   g.hostLaunches++;
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(SGL_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) return fail(SGL_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e));
   return SGL_OK;
 }
 
@@ -320,6 +351,37 @@ int sgl_timer_end(float *ms_out) {
   CU(cudaEventSynchronize(g.evEnd));
   CU(cudaEventElapsedTime(ms_out, g.evBegin, g.evEnd));
   return SGL_OK;
+}
+
+int sgl_set_profiling(int on) {
+  NEED_CTX();
+  gProfiling = on != 0;
+  return SGL_OK;
+}
+
+int sgl_get_kernel_times(SglKernelTime *out, int capacity) {
+  if (!g.ready) return 0;
+  cudaStreamSynchronize(g.stream);
+  int n = 0;
+  for (auto &p : gProf) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p.a, p.b);
+    int k = 0;
+    for (; k < n; k++)
+      if (!strcmp(out[k].name, p.name)) break;
+    if (k == n) {
+      if (n >= capacity) continue;
+      memset(&out[n], 0, sizeof(SglKernelTime));
+      strncpy(out[n].name, p.name, sizeof(out[n].name) - 1);
+      n++;
+    }
+    out[k].launches++;
+    out[k].total_ms += ms;
+    gProfPool.push_back(p.a);
+    gProfPool.push_back(p.b);
+  }
+  gProf.clear();
+  return n;
 }
 
 // ---- reflection ---------------------------------------------------------------------------------------------
@@ -455,7 +517,7 @@ int sgl_texture_upload(int handle, int layer, int level, const void *host_data) 
   CU(cudaMalloc(&tmp, bytes));
   CU(cudaMemcpyAsync(tmp, host_data, bytes, cudaMemcpyHostToDevice, g.stream));
   dim3 blk(16, 16), grd((w + 15) / 16, (h + 15) / 16);
-  int rc = launch(sglRelayoutKernel, grd, blk, (uint32_t *) dst, (const uint32_t *) tmp, w, h, t->obj.layout, 1);
+  int rc = launch("sglRelayoutKernel", sglRelayoutKernel, grd, blk, (uint32_t *) dst, (const uint32_t *) tmp, w, h, t->obj.layout, 1);
   CU(cudaStreamSynchronize(g.stream));
   CU(cudaFree(tmp));
   return rc;
@@ -469,7 +531,7 @@ int sgl_texture_gen_mips(int handle) {
     for (int level = 1; level < t->obj.levels; level++) {
       int w = sglLevelDim(t->obj.width, level), h = sglLevelDim(t->obj.height, level);
       dim3 blk(16, 16), grd((w + 15) / 16, (h + 15) / 16);
-      int rc = launch(sglMipKernel, grd, blk, t->obj, layer, level);
+      int rc = launch("sglMipKernel", sglMipKernel, grd, blk, t->obj, layer, level);
       if (rc) return rc;
     }
   return SGL_OK;
@@ -514,7 +576,7 @@ int sgl_texture_readback(int handle, int layer, int level, int kind, void *host_
   void *tmp = nullptr;
   CU(cudaMalloc(&tmp, need));
   dim3 blk(16, 16), grd((w + 15) / 16, (h + 15) / 16);
-  int rc = launch(sglRelayoutKernel, grd, blk, (uint32_t *) tmp, (const uint32_t *) src, w, h, t->obj.layout, 0);
+  int rc = launch("sglRelayoutKernel", sglRelayoutKernel, grd, blk, (uint32_t *) tmp, (const uint32_t *) src, w, h, t->obj.layout, 0);
   if (rc) return rc;
   CU(cudaStreamSynchronize(g.stream));
   CU(cudaMemcpy(host_out, tmp, need, cudaMemcpyDeviceToHost));
@@ -736,7 +798,7 @@ int sgl_pass_end(void) {
 
   if (nDraws) {
     if (maxVerts > 0) {
-      rc = launch(sglVertexKernel, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws);
+      rc = launch("sglVertexKernel", sglVertexKernel, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws);
       if (rc) return rc;
     }
     if (maxPrims > 0) {
@@ -745,18 +807,20 @@ int sgl_pass_end(void) {
       ss.tileCount = P.tileCount; ss.bigList = P.bigList; ss.bigCount = P.bigCount; ss.bigCapacity = P.bigCapacity;
       ss.counters = g.dCounters; ss.tilesX = tilesX; ss.tilesY = tilesY; ss.fbW = fbW; ss.fbH = fbH;
       ss.tileOwner = P.tileOwner; ss.rank = g.rank;
-      rc = launch(sglSetupKernel, dim3((maxPrims + 127) / 128, nDraws), dim3(128), P.draws, so, ss, dt ? 1 : 0);
+      rc = launch("sglSetupKernel", sglSetupKernel, dim3((maxPrims + 127) / 128, nDraws), dim3(128), P.draws, so, ss, dt ? 1 : 0);
       if (rc) return rc;
     }
   }
-  rc = launch(sglTileScanKernel, dim3(1), dim3(1024), (const uint32_t *) P.tileCount, P.tileOffset, nTiles, g.dCounters);
+  rc = launch("sglTileScanKernel", sglTileScanKernel, dim3(1), dim3(1024), (const uint32_t *) P.tileCount, P.tileOffset, nTiles, g.dCounters);
   if (rc) return rc;
   if (nDraws && maxSlots > 0) {
-    rc = launch(sglBinFillKernel, dim3((maxSlots + 255) / 256, nDraws), dim3(256), P);
+    rc = launch("sglBinFillKernel", sglBinFillKernel, dim3((maxSlots + 255) / 256, nDraws), dim3(256), P);
     if (rc) return rc;
   }
   {
+    profBegin(samples == 4 ? "sglRasterKernel<4>" : "sglRasterKernel<1>");
     int e = samples == 4 ? sglLaunchRaster4(&P, nTiles, (void *) g.stream) : sglLaunchRaster1(&P, nTiles, (void *) g.stream);
+    profEnd();
     g.hostLaunches++;
     if (e != 0) return fail(SGL_ERR_CUDA, "raster kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
   }
@@ -793,7 +857,7 @@ int sgl_kat_barycentric(const float *tri_xyzw, const float *sample_xy, int n, fl
   CU(dTri.alloc(12)); CU(dXy.alloc(2 * n)); CU(dBc.alloc(3 * n)); CU(dZw.alloc(2 * n)); CU(dIn.alloc(n));
   CU(cudaMemcpy(dTri.p, tri_xyzw, 48, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(dXy.p, sample_xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice));
-  int rc = launch(sglKatBarycentricKernel, dim3((n + 127) / 128), dim3(128), (const float *) dTri.p, (const float *) dXy.p, n, dBc.p, dIn.p, dZw.p);
+  int rc = launch("sglKatBarycentricKernel", sglKatBarycentricKernel, dim3((n + 127) / 128), dim3(128), (const float *) dTri.p, (const float *) dXy.p, n, dBc.p, dIn.p, dZw.p);
   if (rc) return rc;
   CU(cudaStreamSynchronize(g.stream));
   CU(cudaMemcpy(bc_out, dBc.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
@@ -817,7 +881,7 @@ int sgl_kat_sample(int texture, int filter_min, int wrap, int border, const floa
   float bf = border == SGL_BORDER_WHITE ? 1.f : 0.f;
   if (t->obj.format == SGL_FMT_FLOAT32) memcpy(&b, &bf, 4);
   else b = border == SGL_BORDER_WHITE ? 0xFFFFFFFFu : 0u;
-  int rc = launch(sglKatSampleKernel, dim3((n + 127) / 128), dim3(128), (const SglTexObj *) g.dTextures, texture, filter_min, wrap, b,
+  int rc = launch("sglKatSampleKernel", sglKatSampleKernel, dim3((n + 127) / 128), dim3(128), (const SglTexObj *) g.dTextures, texture, filter_min, wrap, b,
                   (const float *) dC.p, lod ? (const float *) dL.p : (const float *) nullptr, n, dO.p);
   if (rc) return rc;
   CU(cudaStreamSynchronize(g.stream));
@@ -831,7 +895,7 @@ int sgl_kat_blend(const SglRenderStates *states, const float *src_rgba, const fl
   CU(dS.alloc(4 * n)); CU(dD.alloc(4 * n)); CU(dO.alloc(4 * n));
   CU(cudaMemcpy(dS.p, src_rgba, sizeof(float) * 4 * n, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(dD.p, dst_rgba, sizeof(float) * 4 * n, cudaMemcpyHostToDevice));
-  int rc = launch(sglKatBlendKernel, dim3((n + 127) / 128), dim3(128), *states, (const float *) dS.p, (const float *) dD.p, n, dO.p);
+  int rc = launch("sglKatBlendKernel", sglKatBlendKernel, dim3((n + 127) / 128), dim3(128), *states, (const float *) dS.p, (const float *) dD.p, n, dO.p);
   if (rc) return rc;
   CU(cudaStreamSynchronize(g.stream));
   CU(cudaMemcpy(out_rgba, dO.p, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost));
@@ -845,7 +909,7 @@ int sgl_kat_depth(int func, const float *a, const float *b, int n, int *pass_out
   CU(dA.alloc(n)); CU(dB.alloc(n)); CU(dO.alloc(n));
   CU(cudaMemcpy(dA.p, a, sizeof(float) * n, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(dB.p, b, sizeof(float) * n, cudaMemcpyHostToDevice));
-  int rc = launch(sglKatDepthKernel, dim3((n + 127) / 128), dim3(128), func, (const float *) dA.p, (const float *) dB.p, n, dO.p);
+  int rc = launch("sglKatDepthKernel", sglKatDepthKernel, dim3((n + 127) / 128), dim3(128), func, (const float *) dA.p, (const float *) dB.p, n, dO.p);
   if (rc) return rc;
   CU(cudaStreamSynchronize(g.stream));
   CU(cudaMemcpy(pass_out, dO.p, sizeof(int) * n, cudaMemcpyDeviceToHost));

@@ -182,8 +182,8 @@ def load_gltf(path, image_cache=None):
         pos = accessor(at["POSITION"]).astype(np.float32)
         nrm = accessor(at["NORMAL"]).astype(np.float32) if "NORMAL" in at else None
         uv = accessor(at["TEXCOORD_0"]).astype(np.float32) if "TEXCOORD_0" in at else np.zeros((len(pos), 2), np.float32)
+        # assimp's glTF2 importer flips v once and aiProcess_FlipUVs flips it back: net effect is the file's own v
         uv = uv.copy()
-        uv[:, 1] = 1.0 - uv[:, 1]                       # aiProcess_FlipUVs
         idx = accessor(prim["indices"]).astype(np.int32).reshape(-1) if "indices" in prim \
             else np.arange(len(pos), dtype=np.int32)
         if nrm is None:
