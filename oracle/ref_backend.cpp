@@ -87,6 +87,8 @@ bool readback(Texture &tex, int layer, int level, int kind, Blob &out) {
   return readbackT<float>(tex, layer, level, kind, out);
 }
 
+int nativeHandle(Texture &) { return -1; }
+
 bool loadRaw(Texture &tex, const char *path) {
   if (tex.format == TextureFormat_RGBA8) return dynamic_cast<TextureSoft<RGBA> *>(&tex)->loadFromFile(path);
   return dynamic_cast<TextureSoft<float> *>(&tex)->loadFromFile(path);

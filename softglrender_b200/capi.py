@@ -167,6 +167,10 @@ class Player:
             raise RuntimeError("readback of %s failed (%d)" % (tag, n))
         return out, (w.value, h.value, f.value, s.value)
 
+    def texture_handle(self, tag):
+        self.h.sglp_texture_handle.argtypes = [C.c_void_p, C.c_char_p]
+        return int(self.h.sglp_texture_handle(self.p, tag.encode()))
+
     def close(self):
         if self.p:
             self.h.sglp_destroy(self.p)

@@ -71,7 +71,7 @@ SGL_HD void sglWriteImmediate(const SglPassParams &P, const SglPrim &p, V4 src, 
     const SglRenderStates &rs = P.draws[p.draw].rs;
 #pragma unroll
     for (int s = 0; s < NS; s++)
-      if ((mask >> s) & 1u) st.color[s] = sglPackColor(sglBlend(rs, c, st.color[s]));
+      if ((mask >> s) & 1u) st.color[s] = sglPackColorWrap(sglBlend(rs, c, st.color[s]));
   } else {
     uint32_t pc = sglPackColor(c);
 #pragma unroll

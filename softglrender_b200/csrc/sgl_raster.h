@@ -262,6 +262,16 @@ SGL_HD uint32_t sglPackColor(V4 c) {
   return r | (g << 8) | (b << 16) | (a << 24);
 }
 
+// after blending the reference stores u8vec4(colour * 255.f) WITHOUT clamping again (RendererSoft.cpp:371-374): the
+// float->u8 conversion of an out-of-range value keeps the low byte of the truncated int32 (x86 cvttps2dq + pack)
+SGL_HD uint32_t sglPackColorWrap(V4 c) {
+  uint32_t r = (uint32_t) (int) (c.x * 255.f) & 0xffu;
+  uint32_t g = (uint32_t) (int) (c.y * 255.f) & 0xffu;
+  uint32_t b = (uint32_t) (int) (c.z * 255.f) & 0xffu;
+  uint32_t a = (uint32_t) (int) (c.w * 255.f) & 0xffu;
+  return r | (g << 8) | (b << 16) | (a << 24);
+}
+
 SGL_HD float sglBlendFactorA(float src, float srcA, float dst, float dstA, int factor) {
   switch (factor) {   // calcBlendFactor<float> (BlendSoft.h:14-30)
     case 0: return 0.f;

@@ -32,6 +32,11 @@ bool readback(Texture &tex, int layer, int level, int kind, Blob &out) {
   return t->readPixels((uint32_t) layer, (uint32_t) level, kind, out.data, out.width, out.height);
 }
 
+int nativeHandle(Texture &tex) {
+  auto *t = dynamic_cast<TextureCUDA *>(&tex);
+  return t ? t->handle() : -1;
+}
+
 bool loadRaw(Texture &tex, const char *path) {
   auto *t = dynamic_cast<TextureCUDA *>(&tex);
   return t && t->loadFromFile(path);

@@ -36,6 +36,10 @@ int sglp_readback(void *p, const char *tag, void *dst, size_t cap, int *w, int *
   }
   return (int) (b.data.size() >> 0 > 0x7fffffff ? 0x7fffffff : b.data.size());
 }
+// C-ABI texture handle of the attachment recorded under `tag` (for zero-copy read-back into pinned memory)
+int sglp_texture_handle(void *p, const char *tag) {
+  return static_cast<TracePlayer *>(p)->textureHandleTagged(tag);
+}
 const char *sglp_backend_name(void) { return PlayerBackend::name(); }
 
 }  // extern "C"

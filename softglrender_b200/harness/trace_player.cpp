@@ -118,6 +118,20 @@ bool TracePlayer::readbackTagged(const std::string &tag, PlayerBackend::Blob &ou
   return false;
 }
 
+int TracePlayer::textureHandleTagged(const std::string &tag) {
+  for (int i = frameEnd_ < 0 ? 0 : frameEnd_; i < (int) cmds_.size(); i++) {
+    if (cmds_[i].op != OP_READBACK) continue;
+    Rd r{cmds_[i].p, cmds_[i].p + cmds_[i].n};
+    int tex = r.i32();
+    r.i32();
+    r.i32();
+    if (r.str() != tag) continue;
+    Texture *t = texture(tex);
+    return t ? PlayerBackend::nativeHandle(*t) : -1;
+  }
+  return -1;
+}
+
 bool TracePlayer::exec(const Cmd &c) {
   Rd r{c.p, c.p + c.n};
   switch (c.op) {

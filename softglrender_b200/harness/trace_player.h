@@ -27,6 +27,7 @@ bool loadShaders(SoftGL::ShaderProgram &program, int shading);
 bool readback(SoftGL::Texture &tex, int layer, int level, int kind, Blob &out);
 bool loadRaw(SoftGL::Texture &tex, const char *path);
 bool storeRaw(SoftGL::Texture &tex, const char *path);
+int nativeHandle(SoftGL::Texture &tex);   // C-ABI handle for RendererCUDA, -1 elsewhere
 }  // namespace PlayerBackend
 
 class TracePlayer {
@@ -45,6 +46,8 @@ class TracePlayer {
   SoftGL::Texture *texture(int id) { return id >= 0 && id < (int) textures_.size() ? textures_[id].get() : nullptr; }
   // read-back by tag recorded in the trace tail (bench/e2e): returns false if the tag is unknown
   bool readbackTagged(const std::string &tag, PlayerBackend::Blob &out);
+  // backend-specific integer handle of the texture read back under `tag` (-1 if unknown / not supported)
+  int textureHandleTagged(const std::string &tag);
 
  private:
   struct Cmd {
