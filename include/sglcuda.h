@@ -98,6 +98,8 @@ typedef struct SglCounters {
   uint64_t passes, draws, primitives_in, primitives_binned, fragments_shaded, samples_written;
   uint64_t kernel_launches;   /* launches of kernels defined in this library */
   uint64_t clip_overflow;     /* primitives dropped because the clip-vertex arena was full (should be 0) */
+  uint64_t h2d_bytes;         /* host->device bytes copied by passes (draw records incl. uniform snapshots) and uploads */
+  uint64_t d2h_bytes;         /* device->host bytes copied by read-backs */
 } SglCounters;
 
 /* ---- context ---------------------------------------------------------------------------------------- */

@@ -37,7 +37,8 @@ class SglDraw(C.Structure):
 
 class SglCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("passes", "draws", "primitives_in", "primitives_binned",
-                                          "fragments_shaded", "samples_written", "kernel_launches", "clip_overflow")]
+                                          "fragments_shaded", "samples_written", "kernel_launches", "clip_overflow",
+                                          "h2d_bytes", "d2h_bytes")]
 
 
 class SglKernelTime(C.Structure):

@@ -64,7 +64,7 @@ struct Ctx {
   int ownerTilesX = 0, ownerTilesY = 0;
   // counters
   unsigned long long *dCounters = nullptr;
-  unsigned long long hostLaunches = 0, hostPasses = 0, hostDraws = 0;
+  unsigned long long hostLaunches = 0, hostPasses = 0, hostDraws = 0, hostH2D = 0, hostD2H = 0;
   cudaEvent_t evBegin = nullptr, evEnd = nullptr;
   std::string err;
 };
@@ -328,6 +328,8 @@ int sgl_get_counters(SglCounters *out) {
   out->samples_written = c[5];
   out->kernel_launches = g.hostLaunches;
   out->clip_overflow = c[7];
+  out->h2d_bytes = g.hostH2D;
+  out->d2h_bytes = g.hostD2H;
   return SGL_OK;
 }
 
@@ -335,7 +337,7 @@ int sgl_reset_counters(void) {
   NEED_CTX();
   CU(cudaStreamSynchronize(g.stream));
   CU(cudaMemset(g.dCounters, 0, 8 * sizeof(unsigned long long)));
-  g.hostLaunches = g.hostPasses = g.hostDraws = 0;
+  g.hostLaunches = g.hostPasses = g.hostDraws = g.hostH2D = g.hostD2H = 0;
   return SGL_OK;
 }
 
@@ -508,6 +510,7 @@ int sgl_texture_upload(int handle, int layer, int level, const void *host_data) 
   int w = sglLevelDim(t->obj.width, level), h = sglLevelDim(t->obj.height, level);
   size_t bytes = (size_t) w * h * 4;
   uint8_t *dst = levelPtr(*t, layer, level);
+  g.hostH2D += bytes;
   if (t->obj.layout == SGL_LAYOUT_LINEAR) {
     CU(cudaMemcpyAsync(dst, host_data, bytes, cudaMemcpyHostToDevice, g.stream));
     CU(cudaStreamSynchronize(g.stream));
@@ -564,11 +567,13 @@ int sgl_texture_readback(int handle, int layer, int level, int kind, void *host_
     size_t need = (size_t) w * h * 4;
     if (bytes < need) return fail(SGL_ERR_INVALID, "readback buffer too small");
     CU(cudaMemcpy(host_out, t->obj.resolve, need, cudaMemcpyDeviceToHost));
+    g.hostD2H += need;
     return SGL_OK;
   }
   size_t need = (size_t) w * h * 4 * t->obj.samples;
   if (bytes < need) return fail(SGL_ERR_INVALID, "readback buffer too small");
   uint8_t *src = levelPtr(*t, layer, level);
+  g.hostD2H += need;
   if (t->obj.layout == SGL_LAYOUT_LINEAR) {
     CU(cudaMemcpy(host_out, src, need, cudaMemcpyDeviceToHost));
     return SGL_OK;
@@ -758,6 +763,7 @@ int sgl_pass_end(void) {
     if (rc) return rc;
     memcpy(st->host, g.draws.data(), sizeof(SglDrawRec) * nDraws);
     CU(cudaMemcpyAsync(A + oDraws, st->host, sizeof(SglDrawRec) * nDraws, cudaMemcpyHostToDevice, g.stream));
+    g.hostH2D += sizeof(SglDrawRec) * nDraws;
     CU(cudaEventRecord(st->done, g.stream));
     st->pending = true;
   }
