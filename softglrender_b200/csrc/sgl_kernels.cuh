@@ -9,6 +9,14 @@
 #include <cuda_runtime.h>
 #include "sgl_pixel.h"
 
+// conservative "can primitive p write into tile (tx,ty)?" beyond the bbox overlap; MUST be the same function in the
+// counting pass (sglSetupKernel), the fill pass (sglBinFillKernel) and the big-list scan of the tile kernel
+__device__ __forceinline__ bool sglPrimNearTile(const SglPrim &p, int tx, int ty) {
+  if ((p.flags & SGL_PF_KIND_MASK) == SGL_PK_LINE)
+    return sglLineNearRect(p, tx * SGL_TILE, ty * SGL_TILE, tx * SGL_TILE + SGL_TILE - 1, ty * SGL_TILE + SGL_TILE - 1);
+  return true;
+}
+
 #ifndef SGL_RASTER_ONLY
 // ---------------------------------------------------------------------------------------------------------
 struct SglSetupShared {
@@ -56,6 +64,7 @@ struct SglDeviceAlloc {
       for (int tx = tx0; tx <= tx1; tx++) {
         int t = ty * S.tilesX + tx;
         if (S.tileOwner && S.tileOwner[t] != S.rank) continue;
+        if (!sglPrimNearTile(p, tx, ty)) continue;
         atomicAdd(&S.tileCount[t], 1u);
       }
   }
@@ -163,6 +172,7 @@ __global__ void __launch_bounds__(256) sglBinFillKernel(SglPassParams P) {
     for (int tx = tx0; tx <= tx1; tx++) {
       int t = ty * P.tilesX + tx;
       if (P.tileOwner && P.tileOwner[t] != P.rank) continue;
+      if (!sglPrimNearTile(p, tx, ty)) continue;
       uint32_t pos = P.tileOffset[t] + atomicAdd(&P.tileCursor[t], 1u);
       if (pos < P.binCapacity) P.binSlots[pos] = (uint32_t) slot;
     }
@@ -260,7 +270,7 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS) sglRasterKernel(SglPassParam
         uint32_t key = P.primKeys[slot];
         if (key >= lo && key < hi) {
           const SglPrim &bp = P.prims[slot];
-          if (bp.bx0 <= tx1 && bp.bx1 >= tx0 && bp.by0 <= ty1 && bp.by1 >= ty0) {
+          if (bp.bx0 <= tx1 && bp.bx1 >= tx0 && bp.by0 <= ty1 && bp.by1 >= ty0 && sglPrimNearTile(bp, tx, ty)) {
             int idx = atomicAdd(&sCount, 1);
             if (idx < SGL_SORT_CAP) { sKeys[idx] = key; sSlots[idx] = slot; }
           }

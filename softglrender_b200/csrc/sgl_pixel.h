@@ -146,6 +146,7 @@ SGL_HD void sglPixelPrim(const SglPassParams &P, const SglPrim &p, uint32_t slot
     return;
   }
   // line: every Bresenham step k draws a lineWidth square; visit the steps whose square covers this pixel in order
+  if (!sglLineNearRect(p, px, py, px, py)) return;
   int x0, y0, x1, y1;
   memcpy(&x0, &p.v[0][0], 4); memcpy(&y0, &p.v[0][1], 4); memcpy(&x1, &p.v[0][2], 4); memcpy(&y1, &p.v[0][3], 4);
   const bool steep = (flags & SGL_PF_STEEP) != 0;

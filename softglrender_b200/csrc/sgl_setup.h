@@ -125,7 +125,24 @@ SGL_HD int16_t sglClamp16(int v) { return (int16_t) (v < -32768 ? -32768 : (v > 
 // number of y steps taken before column k is emitted
 SGL_HD int sglLineYSteps(int k, int dx, int ady) {
   if (dx <= 0) return 0;
+  // 2*ady*k + dx - 1 <= 2*32767^2 + 32766 < 2^32: one 32-bit unsigned division covers every on-screen line
+  if (dx < 32768 && ady < 32768 && k >= 0 && k <= dx) return (int) ((2u * (unsigned) ady * (unsigned) k + (unsigned) (dx - 1)) / (2u * (unsigned) dx));
   return (int) (((long long) 2 * ady * k + dx - 1) / ((long long) 2 * dx));
+}
+
+// Conservative test "can any step square of line `p` touch the pixel rectangle [rx0,rx1] x [ry0,ry1]?".  Step k sits at
+// minor = y0 + sy*floor((2*ady*k + dx - 1) / (2*dx)), i.e. within 1 of the ideal line y0 + sy*slope*k (slope <= 1), and its
+// square reaches `reach` pixels, so everything farther than 2*reach + 3 from the ideal line is never written.
+SGL_HD bool sglLineNearRect(const SglPrim &p, int rx0, int ry0, int rx1, int ry1) {
+  int x0, y0, y1;
+  memcpy(&x0, &p.v[0][0], 4); memcpy(&y0, &p.v[0][1], 4); memcpy(&y1, &p.v[0][3], 4);
+  const bool steep = (p.flags & SGL_PF_STEEP) != 0;
+  const int a0 = steep ? ry0 : rx0, a1 = steep ? ry1 : rx1, b0 = steep ? rx0 : ry0, b1 = steep ? rx1 : ry1;
+  const float slope = p.v[2][1];
+  const float margin = (float) (2 * ((int) ceilf(fabsf(p.v[2][0])) + 1) + 3);
+  const float e0 = slope * (float) (a0 - x0), e1 = slope * (float) (a1 - x0);     // slope >= 0: e0 <= e1
+  const float d0 = (float) (y1 > y0 ? b0 - y0 : y0 - b1), d1 = (float) (y1 > y0 ? b1 - y0 : y0 - b0);
+  return !(d1 < e0 - margin || d0 > e1 + margin);
 }
 
 // pixel range covered by rasterizationPoint(centre c, size s) on one axis: [(int)left, (int)right)
@@ -175,6 +192,7 @@ SGL_HD bool sglSetupLine(SglPrim &p, V4 f0, V4 f1, float width, uint32_t stateFl
   memcpy(&p.v[0][0], &x0, 4); memcpy(&p.v[0][1], &y0, 4); memcpy(&p.v[0][2], &x1, 4); memcpy(&p.v[0][3], &y1, 4);
   p.v[1][0] = z0; p.v[1][1] = z1; p.v[1][2] = w0; p.v[1][3] = w1;
   p.v[2][0] = width; p.v[2][1] = p.v[2][2] = p.v[2][3] = 0.f;
+  if (x1 > x0) p.v[2][1] = (float) (y1 > y0 ? y1 - y0 : y0 - y1) / (float) (x1 - x0);   // slope of the ideal line (culling only)
   // conservative pixel bbox of all step squares
   int ylo = y0 < y1 ? y0 : y1, yhi = y0 < y1 ? y1 : y0;
   int a0, a1, b0, b1, t0, t1;

@@ -49,46 +49,60 @@ struct SglSampler {        // BaseSampler state after Sampler2DSoft/SamplerCubeS
   uint32_t border;
 };
 
-// pixelWithWrapMode: returns false when the border colour applies
-SGL_HD bool sglWrapCoord(int &x, int &y, int w, int h, int wrap) {
+// One axis of pixelWithWrapMode (the reference wraps x with the width and y with the height independently).
+// Returns 0 = in range, 1 = border colour applies, 2 = Buffer::get bounds check fails -> T(0).
+SGL_HD int sglWrapAxis(int &x, int n, int wrap) {
   switch (wrap) {
     case SGL_WRAP_REPEAT:
-      // #define CoordMod(i, n) ((i) & ((n) - 1) + (n)) & ((n) - 1)  ==  i & (2n-1) & (n-1)
-      x = (x & ((w - 1) + w)) & (w - 1);
-      y = (y & ((h - 1) + h)) & (h - 1);
-      break;
+      // #define CoordMod(i, n) ((i) & ((n) - 1) + (n)) & ((n) - 1)  ==  i & (2n-1) & (n-1): always inside [0, n-1]
+      x = (x & ((n - 1) + n)) & (n - 1);
+      return 0;
     case SGL_WRAP_MIRRORED_REPEAT:
-      x = (x & ((2 * w - 1) + 2 * w)) & (2 * w - 1);
-      y = (y & ((2 * h - 1) + 2 * h)) & (2 * h - 1);
-      x -= w;
-      y -= h;
+      x = (x & ((2 * n - 1) + 2 * n)) & (2 * n - 1);
+      x -= n;
       x = x >= 0 ? x : (-1 - x);
-      y = y >= 0 ? y : (-1 - y);
-      x = w - 1 - x;
-      y = h - 1 - y;
-      break;
+      x = n - 1 - x;
+      return (unsigned) x >= (unsigned) n ? 2 : 0;
     case SGL_WRAP_CLAMP_TO_EDGE:
-      if (x < 0) x = 0;
-      if (y < 0) y = 0;
-      if (x >= w) x = w - 1;
-      if (y >= h) y = h - 1;
-      break;
+      x = x < 0 ? 0 : (x >= n ? n - 1 : x);
+      return 0;
     case SGL_WRAP_CLAMP_TO_BORDER:
-      if (x < 0 || x >= w) return false;
-      if (y < 0 || y >= h) return false;
-      break;
+      return (x < 0 || x >= n) ? 1 : 0;
   }
-  return true;
+  return (unsigned) x >= (unsigned) n ? 2 : 0;
+}
+
+// pixelWithWrapMode on both axes: returns false when the border colour applies
+SGL_HD bool sglWrapCoord(int &x, int &y, int w, int h, int wrap) {
+  int rx = sglWrapAxis(x, w, wrap), ry = sglWrapAxis(y, h, wrap);
+  return !(rx == 1 || ry == 1);
+}
+
+// one level of one layer, resolved once per filter footprint
+struct SglLevelView {
+  const uint32_t *ptr;
+  int w, h, layout;
+};
+SGL_HD SglLevelView sglLevelView(const SglTexObj *t, int layer, int level) {
+  SglLevelView v;
+  v.w = sglLevelDim(t->width, level);
+  v.h = sglLevelDim(t->height, level);
+  v.layout = t->layout;
+  v.ptr = (const uint32_t *) (t->base + (size_t) layer * t->layerStride + t->levelOffset[level]);
+  return v;
+}
+// texel at wrapped coordinates; rx/ry are the sglWrapAxis results of the two coordinates
+SGL_HD uint32_t sglFetchWrapped(const SglLevelView &lv, uint32_t border, int x, int rx, int y, int ry) {
+  if (rx == 1 || ry == 1) return border;
+  if ((rx | ry) != 0) return 0u;                       // Buffer::get bounds check -> T(0)
+  return SGL_LDG(lv.ptr + sglTexelIndex(lv.layout, lv.w, x, y));
 }
 
 // raw 32-bit texel (RGBA8 packed little-endian or float bits) of layer/level at integer coords with wrap
 SGL_HD uint32_t sglTexel(const SglSampler &s, int layer, int level, int x, int y) {
-  const SglTexObj *t = s.tex;
-  int w = sglLevelDim(t->width, level), h = sglLevelDim(t->height, level);
-  if (!sglWrapCoord(x, y, w, h, s.wrap)) return s.border;
-  if ((unsigned) x >= (unsigned) w || (unsigned) y >= (unsigned) h) return 0u;   // Buffer::get bounds check -> T(0)
-  const uint32_t *p = (const uint32_t *) (t->base + (size_t) layer * t->layerStride + t->levelOffset[level]);
-  return SGL_LDG(p + sglTexelIndex(t->layout, w, x, y));
+  SglLevelView lv = sglLevelView(s.tex, layer, level);
+  int rx = sglWrapAxis(x, lv.w, s.wrap), ry = sglWrapAxis(y, lv.h, s.wrap);
+  return sglFetchWrapped(lv, s.border, x, rx, y, ry);
 }
 
 SGL_HD uint32_t sglMixU8(uint32_t a, uint32_t b, float f, float omf) {
@@ -139,33 +153,37 @@ SGL_HD uint32_t sglMixTexel(int format, uint32_t a, uint32_t b, float f) {
 }
 
 // samplePixelBilinear: uv in texel units of the level
-SGL_HD uint32_t sglPixelBilinear(const SglSampler &s, int layer, int level, float u, float v) {
+SGL_HD uint32_t sglPixelBilinearView(const SglLevelView &lv, int format, int wrap, uint32_t border, float u, float v) {
   float tu = xsub(u, 0.5f), tv = xsub(v, 0.5f);
   float fu = floorf(tu), fv = floorf(tv);
-  int x = (int) fu, y = (int) fv;
-  uint32_t s1 = sglTexel(s, layer, level, x, y);
-  uint32_t s2 = sglTexel(s, layer, level, x + 1, y);
-  uint32_t s3 = sglTexel(s, layer, level, x, y + 1);
-  uint32_t s4 = sglTexel(s, layer, level, x + 1, y + 1);
+  int x0 = (int) fu, y0 = (int) fv;
+  int x1 = x0 + 1, y1 = y0 + 1;
+  int rx0 = sglWrapAxis(x0, lv.w, wrap), rx1 = sglWrapAxis(x1, lv.w, wrap);
+  int ry0 = sglWrapAxis(y0, lv.h, wrap), ry1 = sglWrapAxis(y1, lv.h, wrap);
+  uint32_t s1 = sglFetchWrapped(lv, border, x0, rx0, y0, ry0);
+  uint32_t s2 = sglFetchWrapped(lv, border, x1, rx1, y0, ry0);
+  uint32_t s3 = sglFetchWrapped(lv, border, x0, rx0, y1, ry1);
+  uint32_t s4 = sglFetchWrapped(lv, border, x1, rx1, y1, ry1);
   float fx = xsub(tu, fu), fy = xsub(tv, fv);     // glm::fract(x) = x - floor(x)
-  int fmt = s.tex->format;
-  return sglMixTexel(fmt, sglMixTexel(fmt, s1, s2, fx), sglMixTexel(fmt, s3, s4, fx), fy);
+  return sglMixTexel(format, sglMixTexel(format, s1, s2, fx), sglMixTexel(format, s3, s4, fx), fy);
+}
+SGL_HD uint32_t sglPixelBilinear(const SglSampler &s, int layer, int level, float u, float v) {
+  return sglPixelBilinearView(sglLevelView(s.tex, layer, level), s.tex->format, s.wrap, s.border, u, v);
 }
 
 SGL_HD uint32_t sglSampleNearest(const SglSampler &s, int layer, int level, float u, float v, int ox, int oy) {
-  const SglTexObj *t = s.tex;
-  float w = (float) sglLevelDim(t->width, level), h = (float) sglLevelDim(t->height, level);
-  int x = (int) floorf(xmul(u, w)) + ox;
-  int y = (int) floorf(xmul(v, h)) + oy;
-  return sglTexel(s, layer, level, x, y);
+  SglLevelView lv = sglLevelView(s.tex, layer, level);
+  int x = (int) floorf(xmul(u, (float) lv.w)) + ox;
+  int y = (int) floorf(xmul(v, (float) lv.h)) + oy;
+  int rx = sglWrapAxis(x, lv.w, s.wrap), ry = sglWrapAxis(y, lv.h, s.wrap);
+  return sglFetchWrapped(lv, s.border, x, rx, y, ry);
 }
 
 SGL_HD uint32_t sglSampleBilinear(const SglSampler &s, int layer, int level, float u, float v, int ox, int oy) {
-  const SglTexObj *t = s.tex;
-  float w = (float) sglLevelDim(t->width, level), h = (float) sglLevelDim(t->height, level);
-  float tu = xadd(xmul(u, w), (float) ox);
-  float tv = xadd(xmul(v, h), (float) oy);
-  return sglPixelBilinear(s, layer, level, tu, tv);
+  SglLevelView lv = sglLevelView(s.tex, layer, level);
+  float tu = xadd(xmul(u, (float) lv.w), (float) ox);
+  float tv = xadd(xmul(v, (float) lv.h), (float) oy);
+  return sglPixelBilinearView(lv, s.tex->format, s.wrap, s.border, tu, tv);
 }
 
 // BaseSampler::textureImpl
