@@ -8,14 +8,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "sgl_pixel.h"
-
-// conservative "can primitive p write into tile (tx,ty)?" beyond the bbox overlap; MUST be the same function in the
-// counting pass (sglSetupKernel), the fill pass (sglBinFillKernel) and the big-list scan of the tile kernel
-__device__ __forceinline__ bool sglPrimNearTile(const SglPrim &p, int tx, int ty) {
-  if ((p.flags & SGL_PF_KIND_MASK) == SGL_PK_LINE)
-    return sglLineNearRect(p, tx * SGL_TILE, ty * SGL_TILE, tx * SGL_TILE + SGL_TILE - 1, ty * SGL_TILE + SGL_TILE - 1);
-  return true;
-}
+#include "sgl_vis.cuh"
 
 #ifndef SGL_RASTER_ONLY
 // ---------------------------------------------------------------------------------------------------------
@@ -181,7 +174,9 @@ __global__ void __launch_bounds__(256) sglBinFillKernel(SglPassParams P) {
 #endif  // SGL_RASTER_ONLY
 
 // ---------------------------------------------------------------------------------------------------------
+#ifndef SGL_SORT_CAP
 #define SGL_SORT_CAP 2048
+#endif
 #define SGL_PRIM_BATCH 64
 
 __device__ __forceinline__ void sglBitonicSort(uint32_t *keys, uint32_t *vals, int n /* power of two */) {

@@ -33,6 +33,15 @@ SGL_HD SglShadeEnv sglShadeEnv(const SglPassParams &P) {
 template<int NS>
 SGL_HDN_T V4 sglShadeSlotImpl(SglShadeEnv env, uint32_t slot, int shadeIdx, int px, int py) {
   SglPrim p = env.prims[slot];
+  if ((p.flags & SGL_PF_KIND_MASK) != SGL_PK_TRIANGLE) {
+    // deferred point / line fragment: only recorded for programs without varyings (colour independent of the step)
+    float none[1] = {0.f};
+    SglFsCtx c;
+    c.draw = &env.draws[p.draw];
+    c.textures = env.textures;
+    c.derivValid = false;
+    return sglFragmentShader(c, none);
+  }
   return sglShadeTriangle<NS>(env.draws[p.draw], env.textures, p, env.primVerts[slot], px, py, shadeIdx);
 }
 template<int NS>
@@ -99,6 +108,35 @@ SGL_HD uint32_t sglFlatDepth(const SglPrim &p, float z, bool hasDepth, SglPixelS
   return mask;
 }
 
+// rasterizationLine (RendererSoft.cpp:663-718) seen from one pixel: calls f(t, 1-t, z) for every Bresenham step whose
+// lineWidth square covers (px,py), in step order
+template<class F>
+SGL_HD void sglLineVisit(const SglPrim &p, int px, int py, F &&f) {
+  if (!sglLineNearRect(p, px, py, px, py)) return;
+  const uint32_t flags = p.flags;
+  int x0, y0, x1, y1;
+  memcpy(&x0, &p.v[0][0], 4); memcpy(&y0, &p.v[0][1], 4); memcpy(&x1, &p.v[0][2], 4); memcpy(&y1, &p.v[0][3], 4);
+  const bool steep = (flags & SGL_PF_STEEP) != 0;
+  const float width = p.v[2][0];
+  const int major = steep ? py : px, minor = steep ? px : py;
+  const int dx = x1 - x0, dy = y1 - y0, ady = dy < 0 ? -dy : dy, sy = y1 > y0 ? 1 : -1;
+  int reach = (int) ceilf(fabsf(width)) + 1;
+  int k0 = major - x0 - reach, k1 = major - x0 + reach;
+  if (k0 < 0) k0 = 0;
+  if (k1 > dx) k1 = dx;
+  for (int k = k0; k <= k1; k++) {
+    int cx = x0 + k, cy = y0 + sy * sglLineYSteps(k, dx, ady);
+    int lo, hi;
+    sglPointSpan((float) cx, width, lo, hi);
+    if (major < lo || major > hi) continue;
+    sglPointSpan((float) cy, width, lo, hi);
+    if (minor < lo || minor > hi) continue;
+    float t = xdiv((float) k, (float) dx);           // (float)(x - x0) / (float)dx ; 0/0 = NaN for single-column lines
+    float omt = xsub(1.f, t);
+    f(t, omt, xMix(p.v[1][0], p.v[1][1], t, omt));
+  }
+}
+
 template<int NS>
 SGL_HD void sglPixelPrim(const SglPassParams &P, const SglPrim &p, uint32_t slot, int px, int py, SglPixelState<NS> &st,
                          bool hasColor, bool hasDepth) {
@@ -146,34 +184,14 @@ SGL_HD void sglPixelPrim(const SglPassParams &P, const SglPrim &p, uint32_t slot
     return;
   }
   // line: every Bresenham step k draws a lineWidth square; visit the steps whose square covers this pixel in order
-  if (!sglLineNearRect(p, px, py, px, py)) return;
-  int x0, y0, x1, y1;
-  memcpy(&x0, &p.v[0][0], 4); memcpy(&y0, &p.v[0][1], 4); memcpy(&x1, &p.v[0][2], 4); memcpy(&y1, &p.v[0][3], 4);
-  const bool steep = (flags & SGL_PF_STEEP) != 0;
-  const float width = p.v[2][0];
-  const int major = steep ? py : px, minor = steep ? px : py;
-  const int dx = x1 - x0, dy = y1 - y0, ady = dy < 0 ? -dy : dy, sy = y1 > y0 ? 1 : -1;
-  int reach = (int) ceilf(fabsf(width)) + 1;
-  int k0 = major - x0 - reach, k1 = major - x0 + reach;
-  if (k0 < 0) k0 = 0;
-  if (k1 > dx) k1 = dx;
-  for (int k = k0; k <= k1; k++) {
-    int cx = x0 + k, cy = y0 + sy * sglLineYSteps(k, dx, ady);
-    int lo, hi;
-    sglPointSpan((float) cx, width, lo, hi);
-    if (major < lo || major > hi) continue;
-    sglPointSpan((float) cy, width, lo, hi);
-    if (minor < lo || minor > hi) continue;
-    float t = xdiv((float) k, (float) dx);           // (float)(x - x0) / (float)dx ; 0/0 = NaN for single-column lines
-    float omt = xsub(1.f, t);
-    float z = xMix(p.v[1][0], p.v[1][1], t, omt);
+  sglLineVisit(p, px, py, [&](float t, float omt, float z) {
     uint32_t mask = sglFlatDepth<NS>(p, z, hasDepth, st);
-    if (!mask) continue;
+    if (!mask) return;
     float vary[32];
     const bool sw = (flags & SGL_PF_SWAPPED) != 0;
     const float *va = d.varyings + (size_t) (sw ? pv.i1 : pv.i0) * d.varyingStride;
     const float *vb = d.varyings + (size_t) (sw ? pv.i0 : pv.i1) * d.varyingStride;
     for (int i = 0; i < d.varyingCount; i++) vary[i] = xMix(va[i], vb[i], t, omt);
     sglWriteImmediate<NS>(P, p, sglRunFragmentShader(&d, P.textures, vary), mask, px, py, st);
-  }
+  });
 }

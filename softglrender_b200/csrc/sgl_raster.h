@@ -153,8 +153,11 @@ SGL_HD void sglSampleOffset(int ns, int i, float &ox, float &oy) {
   }
 }
 
-struct SglTriEdge {   // per-triangle part of barycentric()
+struct SglTriEdge {   // per-triangle part of barycentric() + constants of the conservative outside test
   float ax, ay, bx, by, uz, x0, y0;
+  float sax, say, sbx, sby;   // a/b premultiplied by sign(uz)
+  float auz;                  // |uz|
+  float tA, tB;               // |ay| + |ax|, |by| + |bx|
 };
 
 SGL_HD SglTriEdge sglTriEdge(const SglPrim &p) {
@@ -166,7 +169,34 @@ SGL_HD SglTriEdge sglTriEdge(const SglPrim &p) {
   e.bx = xsub(p.v[2][1], e.y0);
   e.by = xsub(p.v[1][1], e.y0);
   e.uz = xfma(e.ax, e.by, -xmul(e.ay, e.bx));
+  const float sg = e.uz < 0.f ? -1.f : 1.f;
+  e.sax = sg * e.ax; e.say = sg * e.ay; e.sbx = sg * e.bx; e.sby = sg * e.by;
+  e.auz = fabsf(e.uz);
+  e.tA = fabsf(e.ay) + fabsf(e.ax);
+  e.tB = fabsf(e.by) + fabsf(e.bx);
   return e;
+}
+
+// Conservative test: true only if barycentric() is CERTAIN to report "outside" for every sample position inside the
+// rectangle (cx +- hx, cy +- hy).  The reference decides on the signs of its float numerators
+//   ux = fma(ay, bz, -rn(az*by)),  uy = fma(az, bx, -rn(ax*bz))        (b2 = ux/uz, b1 = uy/uz, b0 = 1 - (b1 + b2))
+// whose distance from the real-valued affine functions is below 2^-23 * (|ay||bz| + |az||by|) (resp. ax/bx); the test
+// evaluates the same affine functions at the centre in plain float (same error bound), bounds their variation over
+// the rectangle and keeps a 2^-20 relative guard (8x the combined error), so every true outcome here implies the
+// reference's own comparison is negative.  NaNs make every comparison false => "not sure" => exact path.
+SGL_HD bool sglTriSurelyOutside(const SglTriEdge &e, float cx, float cy, float hx, float hy) {
+  const float K = 9.5367431640625e-7f;   // 2^-20
+  float azc = e.x0 - cx, bzc = e.y0 - cy;
+  float sux = e.say * bzc - azc * e.sby;              // sign(uz) * ux at the centre
+  float suy = azc * e.sbx - e.sax * bzc;              // sign(uz) * uy at the centre
+  float aaz = fabsf(azc) + hx + 1.f, abz = fabsf(bzc) + hy + 1.f;
+  float err = K * (e.tA * abz + e.tB * aaz);
+  float rux = hx * fabsf(e.by) + hy * fabsf(e.ay);    // variation of ux / uy over the rectangle
+  float ruy = hx * fabsf(e.bx) + hy * fabsf(e.ax);
+  if (sux < -(rux + err)) return true;                // b2 < 0 everywhere
+  if (suy < -(ruy + err)) return true;                // b1 < 0 everywhere
+  if ((sux + suy) - e.auz > rux + ruy + 2.f * err + K * e.auz) return true;   // b1 + b2 > 1 everywhere
+  return false;
 }
 
 // RendererSoft::barycentric (RendererSoft.cpp:1021-1056) in the oracle binary's association:
@@ -211,6 +241,8 @@ template<int NS>
 SGL_HD uint32_t sglCoverTriangle(const SglPrim &p, const SglTriEdge &e, int px, int py, const float *depth, bool hasDepth,
                                  float *zOut, int &shadeIdx) {
   float fx = (float) px, fy = (float) py;
+  // all sample positions (and the centre) lie within +-0.375 of the pixel centre
+  if (sglTriSurelyOutside(e, fx + 0.5f, fy + 0.5f, NS > 1 ? 0.375f : 0.f, NS > 1 ? 0.375f : 0.f)) return 0;
   uint32_t geo = 0;
   float bc[NS][3];
 #pragma unroll

@@ -1,0 +1,6 @@
+// Deferred shading kernel for single-sample targets (own translation unit: the fragment shaders dominate ptxas time).
+#include "sgl_vis.cuh"
+extern "C" int sglLaunchShade1(const SglPassParams *P, int nTiles, void *stream) {
+  sglShadeKernel<1><<<dim3(nTiles), dim3(SGL_TILE_THREADS), 0, (cudaStream_t) stream>>>(*P);
+  return (int) cudaGetLastError();
+}

@@ -96,6 +96,7 @@ struct SglPassParams {
   uint8_t *colorBase;       // RGBA8 [y][x][sample] of the attached layer/level, or null
   float *depthBase;         // float [y][x][sample], or null
   uint8_t *resolveBase;     // resolved colour (MS only), or null
+  uint32_t *vis;            // visibility buffer of the deferred path: owner (slot | shading sample << 29) [y][x][sample]
   int32_t fbW, fbH, samples;
   int32_t clearColorFlag, clearDepthFlag;
   uint32_t clearColor;      // RGBA8 packed (RendererSoft.cpp:72-75)

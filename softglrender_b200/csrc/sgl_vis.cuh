@@ -1,0 +1,308 @@
+// Deferred ("visibility buffer") form of the tile rasteriser, used for every render pass whose draws are all opaque:
+//   sglVisKernel<NS>    one CTA per 16x16 tile, one thread per pixel: ordered walk over the tile's primitives doing
+//                       exact coverage + depth only; writes per-sample depth and per-sample OWNER (primitive slot +
+//                       shading sample) -- no shading code, so it runs at 4 CTAs/SM instead of 2
+//   sglShadeKernel<NS>  one thread per pixel: shades each distinct owner once (fragment shaders + texturing),
+//                       packs, resolves MSAA and writes colour -- no barriers, no shared memory
+// Exactness argument: DESIGN.md section 5 (an opaque fragment's colour is a pure function of (primitive, pixel), and the
+// last fragment to pass the depth test per sample is the one whose colour survives in the reference).
+// Passes with blending or with point/line draws of programs that have varyings use the fused sglRasterKernel instead.
+#pragma once
+#include <cuda_runtime.h>
+#include "sgl_pixel.h"
+
+#ifndef SGL_SORT_CAP
+#define SGL_SORT_CAP 2048
+#endif
+#define SGL_VIS_BATCH 64
+
+// conservative "can primitive p write into tile (tx,ty)?" beyond the bbox overlap; MUST be the same function in the
+// counting pass (sglSetupKernel), the fill pass (sglBinFillKernel) and the big-list scan of the tile kernels
+__device__ __forceinline__ bool sglPrimNearTile(const SglPrim &p, int tx, int ty) {
+  const uint32_t kind = p.flags & SGL_PF_KIND_MASK;
+  if (kind == SGL_PK_LINE)
+    return sglLineNearRect(p, tx * SGL_TILE, ty * SGL_TILE, tx * SGL_TILE + SGL_TILE - 1, ty * SGL_TILE + SGL_TILE - 1);
+  if (kind == SGL_PK_TRIANGLE) {
+    // every sample position of the tile lies within +-SGL_TILE/2 of its centre
+    SglTriEdge e = sglTriEdge(p);
+    const float h = 0.5f * SGL_TILE;
+    return !sglTriSurelyOutside(e, (float) (tx * SGL_TILE) + h, (float) (ty * SGL_TILE) + h, h, h);
+  }
+  return true;
+}
+
+struct __align__(16) SglVisPrim {   // shared-memory form of a primitive: record + per-triangle edge constants
+  SglPrim p;
+  SglTriEdge e;
+  float pad[2];
+};
+
+__device__ __forceinline__ void sglBitonicSortKV(uint32_t *keys, uint32_t *vals, int n /* power of two */) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          uint32_t a = keys[i], b = keys[ixj];
+          bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            keys[i] = b; keys[ixj] = a;
+            uint32_t t = vals[i]; vals[i] = vals[ixj]; vals[ixj] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Sorts (keys, vals)[0..n) by key; keys are unique.  n <= blockDim.x: rank sort (each thread counts the keys below its
+// own: n broadcast shared-memory reads, two barriers); larger lists: bitonic network.  Ends with a barrier.
+__device__ __forceinline__ void sglSortTileList(uint32_t *keys, uint32_t *vals, int n) {
+  if (n <= 1) return;
+  if (n <= (int) blockDim.x) {
+    const int i = threadIdx.x;
+    uint32_t k = 0, v = 0;
+    int rank = 0;
+    if (i < n) {
+      k = keys[i];
+      v = vals[i];
+      for (int j = 0; j < n; j++) rank += keys[j] < k ? 1 : 0;
+    }
+    __syncthreads();
+    if (i < n) { keys[rank] = k; vals[rank] = v; }
+    __syncthreads();
+    return;
+  }
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  for (int i = n + threadIdx.x; i < n2; i += blockDim.x) { keys[i] = 0xFFFFFFFFu; vals[i] = 0; }
+  __syncthreads();
+  sglBitonicSortKV(keys, vals, n2);
+}
+
+// one primitive against one pixel: coverage + depth, owners instead of colours
+template<int NS>
+__device__ __forceinline__ void sglVisPixelPrim(const SglPassParams &P, const SglVisPrim &vp, uint32_t slot, int px, int py,
+                                                float (&depth)[NS], uint32_t (&owner)[NS], bool hasColor, bool hasDepth) {
+  const SglPrim &p = vp.p;
+  if (px < p.bx0 || px > p.bx1 || py < p.by0 || py > p.by1) return;
+  const uint32_t flags = p.flags;
+  const uint32_t kind = flags & SGL_PF_KIND_MASK;
+  if (kind == SGL_PK_TRIANGLE) {
+    if (flags & SGL_PF_IRREGULAR) {
+      const SglDrawRec &d = P.draws[p.draw];
+      int q;
+      if (!sglAxisVisitedExact(min3f(p.v[0][0], p.v[1][0], p.v[2][0]), max3f(p.v[0][0], p.v[1][0], p.v[2][0]), d.vpW, px, q)) return;
+      if (!sglAxisVisitedExact(min3f(p.v[0][1], p.v[1][1], p.v[2][1]), max3f(p.v[0][1], p.v[1][1], p.v[2][1]), d.vpH, py, q)) return;
+    }
+    float z[NS];
+    int shadeIdx = 0;
+    uint32_t mask = sglCoverTriangle<NS>(p, vp.e, px, py, depth, hasDepth, z, shadeIdx);
+    if (!mask) return;
+    const bool wr = (flags & SGL_PF_DEPTH_TEST) && (flags & SGL_PF_DEPTH_MASK);
+    const uint32_t o = sglOwner(slot, shadeIdx);
+#pragma unroll
+    for (int s = 0; s < NS; s++)
+      if ((mask >> s) & 1u) {
+        if (wr) depth[s] = z[s];
+        owner[s] = o;
+      }
+    return;
+  }
+  if (!hasColor) return;   // rasterizationPoint returns without a colour buffer (RendererSoft.cpp:636-640)
+  SglPixelState<NS> st;    // only the depth part is live
+#pragma unroll
+  for (int s = 0; s < NS; s++) st.depth[s] = depth[s];
+  uint32_t wrote = 0;
+  if (kind == SGL_PK_POINT) {
+    wrote = sglFlatDepth<NS>(p, p.v[0][2], hasDepth, st);
+  } else {
+    sglLineVisit(p, px, py, [&](float, float, float z) { wrote |= sglFlatDepth<NS>(p, z, hasDepth, st); });
+  }
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    depth[s] = st.depth[s];
+    if ((wrote >> s) & 1u) owner[s] = sglOwner(slot, 0);
+  }
+}
+
+template<int NS>
+__global__ void __launch_bounds__(SGL_TILE_THREADS, 4) sglVisKernel(SglPassParams P) {
+  __shared__ uint32_t sKeys[SGL_SORT_CAP];
+  __shared__ uint32_t sSlots[SGL_SORT_CAP];
+  __shared__ SglVisPrim sPrims[SGL_VIS_BATCH];
+  __shared__ int sCount;
+
+  const int tile = blockIdx.x;
+  if (P.tileOwner && P.tileOwner[tile] != P.rank) return;
+  const int tx = tile % P.tilesX, ty = tile / P.tilesX;
+  const int tid = threadIdx.x;
+  const int px = tx * SGL_TILE + (tid & (SGL_TILE - 1));
+  const int py = ty * SGL_TILE + (tid / SGL_TILE);
+  const bool inFb = px < P.fbW && py < P.fbH;
+  const bool hasColor = P.colorBase != nullptr, hasDepth = P.depthBase != nullptr;
+  const size_t pix = (size_t) py * P.fbW + px;
+
+  float depth[NS];
+  uint32_t owner[NS];
+#pragma unroll
+  for (int s = 0; s < NS; s++) { depth[s] = P.clearDepth; owner[s] = SGL_OWNER_NONE; }
+  if (inFb && hasDepth && !P.clearDepthFlag) {
+    if (NS == 4) {
+      float4 dq = reinterpret_cast<const float4 *>(P.depthBase)[pix];
+      depth[0] = dq.x; depth[NS > 1 ? 1 : 0] = dq.y; depth[NS > 2 ? 2 : 0] = dq.z; depth[NS > 3 ? 3 : 0] = dq.w;
+    } else depth[0] = P.depthBase[pix];
+  }
+
+  const uint32_t off = P.tileOffset[tile];
+  uint32_t nList = P.tileOffset[tile + 1] - off;
+  if (off + nList > P.binCapacity) nList = off < P.binCapacity ? P.binCapacity - off : 0;
+  uint32_t nBig = *P.bigCount;
+  if (nBig > P.bigCapacity) nBig = P.bigCapacity;
+  const int tx0 = tx * SGL_TILE, ty0 = ty * SGL_TILE, tx1 = tx0 + SGL_TILE - 1, ty1 = ty0 + SGL_TILE - 1;
+
+  // key windows: the common case (everything fits) is one window covering all keys
+  uint32_t lo = 0;
+  const uint32_t keyEnd = 0xFFFFFFFFu;
+  const bool fits = (nList + nBig) <= SGL_SORT_CAP;
+  while (true) {
+    uint32_t hi = keyEnd;
+    while (true) {   // gather candidates with lo <= key < hi
+      if (tid == 0) sCount = 0;
+      __syncthreads();
+      for (uint32_t i = tid; i < nList; i += SGL_TILE_THREADS) {
+        uint32_t slot = P.binSlots[off + i];
+        uint32_t key = P.primKeys[slot];
+        if (key >= lo && key < hi) {
+          int idx = atomicAdd(&sCount, 1);
+          if (idx < SGL_SORT_CAP) { sKeys[idx] = key; sSlots[idx] = slot; }
+        }
+      }
+      for (uint32_t i = tid; i < nBig; i += SGL_TILE_THREADS) {
+        uint32_t slot = P.bigList[i];
+        uint32_t key = P.primKeys[slot];
+        if (key >= lo && key < hi) {
+          const SglPrim &bp = P.prims[slot];
+          if (bp.bx0 <= tx1 && bp.bx1 >= tx0 && bp.by0 <= ty1 && bp.by1 >= ty0 && sglPrimNearTile(bp, tx, ty)) {
+            int idx = atomicAdd(&sCount, 1);
+            if (idx < SGL_SORT_CAP) { sKeys[idx] = key; sSlots[idx] = slot; }
+          }
+        }
+      }
+      __syncthreads();
+      if (sCount <= SGL_SORT_CAP) break;
+      hi = lo + (hi - lo) / 2;          // too many: halve the key window and retry
+      __syncthreads();
+    }
+    const int n = sCount;
+    sglSortTileList(sKeys, sSlots, n);
+    for (int b0 = 0; b0 < n; b0 += SGL_VIS_BATCH) {   // process in order
+      const int nb = n - b0 < SGL_VIS_BATCH ? n - b0 : SGL_VIS_BATCH;
+      __syncthreads();
+      {  // 64 records x 4 x uint4 = one 16-byte load per thread, then one thread per record derives the edge constants
+        const int r = tid >> 2, q = tid & 3;
+        if (r < nb) {
+          const uint4 *src = reinterpret_cast<const uint4 *>(P.prims + sSlots[b0 + r]);
+          reinterpret_cast<uint4 *>(&sPrims[r].p)[q] = __ldg(src + q);
+        }
+      }
+      __syncthreads();
+      if (tid < nb && (sPrims[tid].p.flags & SGL_PF_KIND_MASK) == SGL_PK_TRIANGLE) sPrims[tid].e = sglTriEdge(sPrims[tid].p);
+      __syncthreads();
+      if (inFb) {
+        for (int k = 0; k < nb; k++) sglVisPixelPrim<NS>(P, sPrims[k], sSlots[b0 + k], px, py, depth, owner, hasColor, hasDepth);
+      }
+    }
+    __syncthreads();
+    if (fits || hi == keyEnd) break;
+    lo = hi;
+  }
+
+  if (inFb) {
+    if (hasDepth) {
+      if (NS == 4) reinterpret_cast<float4 *>(P.depthBase)[pix] =
+          make_float4(depth[0], depth[NS > 1 ? 1 : 0], depth[NS > 2 ? 2 : 0], depth[NS > 3 ? 3 : 0]);
+      else P.depthBase[pix] = depth[0];
+    }
+    if (hasColor) {
+      if (NS == 4) reinterpret_cast<uint4 *>(P.vis)[pix] =
+          make_uint4(owner[0], owner[NS > 1 ? 1 : 0], owner[NS > 2 ? 2 : 0], owner[NS > 3 ? 3 : 0]);
+      else P.vis[pix] = owner[0];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// grid = tiles (same ownership rule as the visibility kernel); a warp shades an 8x4 pixel block
+template<int NS>
+__global__ void __launch_bounds__(SGL_TILE_THREADS) sglShadeKernel(SglPassParams P) {
+  const int tile = blockIdx.x;
+  if (P.tileOwner && P.tileOwner[tile] != P.rank) return;
+  const int tx = tile % P.tilesX, ty = tile / P.tilesX;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int px = tx * SGL_TILE + (warp & 1) * 8 + (lane & 7);
+  const int py = ty * SGL_TILE + (warp >> 1) * 4 + (lane >> 3);
+  const bool inFb = px < P.fbW && py < P.fbH;
+  const size_t pix = (size_t) py * P.fbW + px;
+
+  uint32_t owner[NS], color[NS];
+#pragma unroll
+  for (int s = 0; s < NS; s++) { owner[s] = SGL_OWNER_NONE; color[s] = P.clearColor; }
+  if (inFb) {
+    if (NS == 4) {
+      uint4 o = reinterpret_cast<const uint4 *>(P.vis)[pix];
+      owner[0] = o.x; owner[NS > 1 ? 1 : 0] = o.y; owner[NS > 2 ? 2 : 0] = o.z; owner[NS > 3 ? 3 : 0] = o.w;
+      if (!P.clearColorFlag) {
+        uint4 cq = reinterpret_cast<const uint4 *>(P.colorBase)[pix];
+        color[0] = cq.x; color[NS > 1 ? 1 : 0] = cq.y; color[NS > 2 ? 2 : 0] = cq.z; color[NS > 3 ? 3 : 0] = cq.w;
+      }
+    } else {
+      owner[0] = P.vis[pix];
+      if (!P.clearColorFlag) color[0] = reinterpret_cast<const uint32_t *>(P.colorBase)[pix];
+    }
+  }
+
+  // warp-coherent by draw: lanes shade together when their pending owner belongs to the draw of the warp's smallest
+  // pending slot (slots are laid out draw by draw)
+  unsigned int shaded = 0;
+  while (true) {
+    uint32_t best = SGL_OWNER_NONE, bestSlot = 0xFFFFFFFFu;
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+      uint32_t o = owner[s];
+      if (o != SGL_OWNER_NONE && (o & 0x1fffffffu) < bestSlot) { best = o; bestSlot = o & 0x1fffffffu; }
+    }
+    uint32_t wmin = __reduce_min_sync(0xffffffffu, bestSlot);
+    if (wmin == 0xFFFFFFFFu) break;
+    uint32_t wdraw = P.prims[wmin].draw;
+    if (best != SGL_OWNER_NONE && P.prims[bestSlot].draw == wdraw) {
+      uint32_t c = sglPackColor(sglShadeSlot<NS>(P, bestSlot, (int) (best >> 29), px, py));
+      shaded++;
+#pragma unroll
+      for (int s = 0; s < NS; s++)
+        if (owner[s] == best) { color[s] = c; owner[s] = SGL_OWNER_NONE; }
+    }
+  }
+
+  if (inFb) {
+    if (NS == 4) {
+      reinterpret_cast<uint4 *>(P.colorBase)[pix] = make_uint4(color[0], color[NS > 1 ? 1 : 0], color[NS > 2 ? 2 : 0], color[NS > 3 ? 3 : 0]);
+      if (P.resolveBase) {   // multiSampleResolve (RendererSoft.cpp:880-912): u8vec4(sum / 4.f) == exact integer division
+        uint32_t r = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          uint32_t sum = 0;
+#pragma unroll
+          for (int s = 0; s < NS; s++) sum += (color[s] >> (8 * c)) & 0xffu;
+          r |= (sum / NS) << (8 * c);
+        }
+        reinterpret_cast<uint32_t *>(P.resolveBase)[pix] = r;
+      }
+    } else {
+      reinterpret_cast<uint32_t *>(P.colorBase)[pix] = color[0];
+    }
+  }
+  shaded = __reduce_add_sync(0xffffffffu, shaded);
+  if (lane == 0 && shaded) atomicAdd(P.counters + 4, (unsigned long long) shaded);
+}

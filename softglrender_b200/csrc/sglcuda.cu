@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -15,6 +16,10 @@
 // tile rasteriser instantiations live in their own translation units (sgl_raster_ns{1,4}.cu)
 extern "C" int sglLaunchRaster1(const SglPassParams *P, int nTiles, void *stream);
 extern "C" int sglLaunchRaster4(const SglPassParams *P, int nTiles, void *stream);
+// deferred path: visibility kernels (sgl_vis.cu) and shading kernels (sgl_shade_ns{1,4}.cu)
+extern "C" int sglLaunchVis(int samples, const SglPassParams *P, int nTiles, void *stream);
+extern "C" int sglLaunchShade1(const SglPassParams *P, int nTiles, void *stream);
+extern "C" int sglLaunchShade4(const SglPassParams *P, int nTiles, void *stream);
 
 namespace {
 
@@ -57,6 +62,9 @@ struct Ctx {
   // arena
   uint8_t *arena = nullptr;
   size_t arenaCap = 0;
+  uint32_t *vis = nullptr;     // visibility buffer of the deferred path
+  size_t visCap = 0;
+  int forceFused = 0;          // SGL_FORCE_FUSED=1: always use the fused tile kernel (A/B runs, tests)
   Staging staging[4];
   int stagingNext = 0;
   // multi-GPU
@@ -266,6 +274,10 @@ int sgl_init(int device_ordinal, int rank, int world) {
   CU(cudaMemset(g.dCounters, 0, 8 * sizeof(unsigned long long)));
   CU(cudaEventCreate(&g.evBegin));
   CU(cudaEventCreate(&g.evEnd));
+  {
+    const char *ff = getenv("SGL_FORCE_FUSED");
+    g.forceFused = (ff && atoi(ff) != 0) ? 1 : 0;
+  }
   g.ready = true;
   g.err.clear();
   return SGL_OK;
@@ -282,6 +294,7 @@ int sgl_shutdown(void) {
   }
   if (g.dTextures) cudaFree(g.dTextures);
   if (g.arena) cudaFree(g.arena);
+  if (g.vis) cudaFree(g.vis);
   if (g.dTileOwner) cudaFree(g.dTileOwner);
   if (g.dCounters) cudaFree(g.dCounters);
   for (auto &s : g.staging) {
@@ -823,7 +836,42 @@ int sgl_pass_end(void) {
     rc = launch("sglBinFillKernel", sglBinFillKernel, dim3((maxSlots + 255) / 256, nDraws), dim3(256), P);
     if (rc) return rc;
   }
-  {
+  // Deferred (visibility + shading) path for passes made of opaque draws whose point/line programs have no varyings;
+  // everything else (blending, wireframe with a lit program) takes the fused tile kernel.
+  bool deferred = !g.forceFused;
+  for (int i = 0; i < nDraws && deferred; i++) {
+    const SglDrawRec &r = g.draws[i];
+    const bool fill = r.rs.primitive_type == SGL_PRIM_TRIANGLE && r.rs.polygon_mode == SGL_POLY_FILL;
+    if (r.rs.blend && ct) deferred = false;
+    if (!fill && r.varyingCount != 0) deferred = false;
+  }
+  if (deferred) {
+    if (ct) {
+      size_t need = (size_t) fbW * fbH * samples * sizeof(uint32_t);
+      if (need > g.visCap) {
+        CU(cudaStreamSynchronize(g.stream));
+        if (g.vis) CU(cudaFree(g.vis));
+        g.vis = nullptr;
+        g.visCap = 0;
+        cudaError_t e = cudaMalloc(&g.vis, need);
+        if (e != cudaSuccess) return fail(SGL_ERR_OOM, "visibility buffer of %zu bytes: %s", need, cudaGetErrorString(e));
+        g.visCap = need;
+      }
+      P.vis = g.vis;
+    }
+    profBegin(samples == 4 ? "sglVisKernel<4>" : "sglVisKernel<1>");
+    int e = sglLaunchVis(samples, &P, nTiles, (void *) g.stream);
+    profEnd();
+    g.hostLaunches++;
+    if (e != 0) return fail(SGL_ERR_CUDA, "visibility kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
+    if (ct) {
+      profBegin(samples == 4 ? "sglShadeKernel<4>" : "sglShadeKernel<1>");
+      e = samples == 4 ? sglLaunchShade4(&P, nTiles, (void *) g.stream) : sglLaunchShade1(&P, nTiles, (void *) g.stream);
+      profEnd();
+      g.hostLaunches++;
+      if (e != 0) return fail(SGL_ERR_CUDA, "shading kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
+    }
+  } else {
     profBegin(samples == 4 ? "sglRasterKernel<4>" : "sglRasterKernel<1>");
     int e = samples == 4 ? sglLaunchRaster4(&P, nTiles, (void *) g.stream) : sglLaunchRaster1(&P, nTiles, (void *) g.stream);
     profEnd();
