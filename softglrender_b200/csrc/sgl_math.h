@@ -32,6 +32,19 @@ SGL_HD float xfma(float a, float b, float c) { return fmaf(a, b, c); }
 SGL_HD float xdiv(float a, float b) { volatile float r = a / b; return r; }
 #endif
 
+// Shading-only arithmetic (lighting maths of the fragment shaders): colour has a 1/255 tolerance, so the device uses
+// the SFU forms (MUFU.RCP / RSQ / LG2 / EX2); -DSGL_PRECISE_SHADING restores IEEE division, sqrt and libm pow.
+// Coverage, depth, interpolation and texel arithmetic never go through these.
+#if defined(__CUDA_ARCH__) && !defined(SGL_PRECISE_SHADING)
+SGL_HD float sdiv(float a, float b) { return __fdividef(a, b); }
+SGL_HD float srsqrt(float a) { return rsqrtf(a); }
+SGL_HD float spow(float a, float e) { return __powf(a, e); }
+#else
+SGL_HD float sdiv(float a, float b) { return a / b; }
+SGL_HD float srsqrt(float a) { return 1.0f / sqrtf(a); }
+SGL_HD float spow(float a, float e) { return powf(a, e); }
+#endif
+
 struct V2 { float x, y; };
 struct V3 { float x, y, z; };
 struct V4 { float x, y, z, w; };
@@ -46,15 +59,16 @@ SGL_HD V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
 SGL_HD V3 operator*(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
 SGL_HD V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
 SGL_HD V3 operator*(float s, V3 a) { return v3(a.x * s, a.y * s, a.z * s); }
-SGL_HD V3 operator/(V3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
-SGL_HD V3 operator/(V3 a, V3 b) { return v3(a.x / b.x, a.y / b.y, a.z / b.z); }
+SGL_HD V3 operator/(V3 a, float s) { return v3(sdiv(a.x, s), sdiv(a.y, s), sdiv(a.z, s)); }
+SGL_HD V3 operator/(V3 a, V3 b) { return v3(sdiv(a.x, b.x), sdiv(a.y, b.y), sdiv(a.z, b.z)); }
 SGL_HD float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 SGL_HD float dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
 SGL_HD V3 cross(V3 a, V3 b) { return v3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
-SGL_HD V3 normalize(V3 a) { float inv = 1.0f / sqrtf(dot(a, a)); return a * inv; }   // glm: v * inversesqrt(dot(v,v))
+SGL_HD V3 normalize(V3 a) { float inv = srsqrt(dot(a, a)); return a * inv; }
+SGL_HD V3 normalizeP(V3 a) { float inv = 1.0f / sqrtf(dot(a, a)); return a * inv; }   // IEEE form (IBL generation passes)   // glm: v * inversesqrt(dot(v,v))
 SGL_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 SGL_HD V3 vmax(V3 a, V3 b) { return v3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
-SGL_HD V3 vpow(V3 a, float e) { return v3(powf(a.x, e), powf(a.y, e), powf(a.z, e)); }
+SGL_HD V3 vpow(V3 a, float e) { return v3(spow(a.x, e), spow(a.y, e), spow(a.z, e)); }
 SGL_HD V3 vmix(V3 a, V3 b, float t) { return a * (1.0f - t) + b * t; }
 SGL_HD V3 reflect(V3 I, V3 N) { return I - N * dot(N, I) * 2.0f; }
 

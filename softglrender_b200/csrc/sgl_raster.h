@@ -388,6 +388,23 @@ SGL_HD int sglPickShadingSample(const SglTriEdge &e, int px, int py) {
 SGL_HD void sglInterpVaryings(float *out, const float *in0, const float *in1, const float *in2, int n, const float *bc) {
   for (int i = 0; i < n; i++) out[i] = xfma(in2[i], bc[2], xfma(in1[i], bc[1], xmul(in0[i], bc[0])));
 }
+// fixed-size form (N multiple of 4, rows are 32-byte aligned): 128-bit loads, fully unrolled so the result stays in registers
+template<int N>
+SGL_HD void sglInterpVaryingsN(float *out, const float *in0, const float *in1, const float *in2, const float *bc) {
+#if defined(__CUDA_ARCH__)
+  const float4 *a = reinterpret_cast<const float4 *>(in0), *b = reinterpret_cast<const float4 *>(in1), *c = reinterpret_cast<const float4 *>(in2);
+#pragma unroll
+  for (int i = 0; i < N / 4; i++) {
+    float4 x = __ldg(a + i), y = __ldg(b + i), z = __ldg(c + i);
+    out[4 * i + 0] = xfma(z.x, bc[2], xfma(y.x, bc[1], xmul(x.x, bc[0])));
+    out[4 * i + 1] = xfma(z.y, bc[2], xfma(y.y, bc[1], xmul(x.y, bc[0])));
+    out[4 * i + 2] = xfma(z.z, bc[2], xfma(y.z, bc[1], xmul(x.z, bc[0])));
+    out[4 * i + 3] = xfma(z.w, bc[2], xfma(y.w, bc[1], xmul(x.w, bc[0])));
+  }
+#else
+  sglInterpVaryings(out, in0, in1, in2, N, bc);
+#endif
+}
 
 SGL_HD bool sglDrawNeedsDeriv(const SglDrawRec &d) {
   if (d.shader != SGL_SHADER_PBR && d.shader != SGL_SHADER_BLINNPHONG) return false;
@@ -404,13 +421,17 @@ SGL_HD V4 sglShadeTriangle(const SglDrawRec &d, const SglTexObj *textures, const
   SglTriEdge e = sglTriEdge(p);
   float bc[3], spx, spy, z, w;
   sglShadingBarycentric<NS>(p, e, px, py, shadeIdx, bc, spx, spy, z, w);
-  const int n = d.varyingCount;
   const int stride = d.varyingStride;
   float vary[32];
   const float *in0 = d.varyings + (size_t) pv.i0 * stride;
   const float *in1 = d.varyings + (size_t) pv.i1 * stride;
   const float *in2 = d.varyings + (size_t) pv.i2 * stride;
-  sglInterpVaryings(vary, in0, in1, in2, n, bc);
+  switch (d.shader) {   // sizeof(ShaderVaryings) of each program, rounded up to whole float4s (rows are padded to 8 floats)
+    case SGL_SHADER_PBR: sglInterpVaryingsN<28>(vary, in0, in1, in2, bc); break;
+    case SGL_SHADER_BLINNPHONG: sglInterpVaryingsN<32>(vary, in0, in1, in2, bc); break;
+    case SGL_SHADER_BASIC: break;
+    default: sglInterpVaryingsN<4>(vary, in0, in1, in2, bc); break;   // skybox / IBL: vec3 position; FXAA: vec2
+  }
   SglFsCtx c;
   c.draw = &d;
   c.textures = textures;

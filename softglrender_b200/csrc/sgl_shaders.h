@@ -211,7 +211,7 @@ SGL_HD V4 sglFsBlinnPhong(const SglFsCtx &c, const float *v) {
     V3 camDir = normalize(v3(v[12], v[13], v[14]));
     V3 H = normalize(L + camDir);
     float sa = fmaxf(dot(N, H), 0.0f);
-    specular = v3s(uF(d, 336) * powf(sa, 128.f));
+    specular = v3s(uF(d, 336) * spow(sa, 128.f));
     if (uI(d, 328)) {
       float shadow = 1.0f - sglShadowCalc(c, v4(v[20], v[21], v[22], v[23]), N, lightVec);
       diffuse = diffuse * shadow;
@@ -235,12 +235,21 @@ SGL_HD float sglDistributionGGX(V3 N, V3 H, float roughness) {
   float NdotH2 = NdotH * NdotH;
   float denom = (NdotH2 * (a2 - 1.0f) + 1.0f);
   denom = SGL_PI * denom * denom;
+  return sdiv(a2, denom);
+}
+SGL_HD float sglDistributionGGXP(V3 N, V3 H, float roughness) {   // IEEE division (IBL prefilter pass)
+  float a = roughness * roughness;
+  float a2 = a * a;
+  float NdotH = fmaxf(dot(N, H), 0.0f);
+  float NdotH2 = NdotH * NdotH;
+  float denom = (NdotH2 * (a2 - 1.0f) + 1.0f);
+  denom = SGL_PI * denom * denom;
   return a2 / denom;
 }
 SGL_HD float sglGeometrySchlickGGX(float NdotV, float roughness) {
   float r = roughness + 1.0f;
   float k = (r * r) / 8.0f;
-  return NdotV / (NdotV * (1.0f - k) + k);
+  return sdiv(NdotV, NdotV * (1.0f - k) + k);
 }
 SGL_HD float sglGeometrySmith(V3 N, V3 V, V3 L, float roughness) {
   float NdotV = fmaxf(dot(N, V), 0.0f), NdotL = fmaxf(dot(N, L), 0.0f);
@@ -281,7 +290,7 @@ SGL_HD V4 sglFsPbr(const SglFsCtx &c, const float *v) {
     V3 radiance = uV3(d, 304) * atten;
     float NDF = sglDistributionGGX(N, H, roughness);
     float G = sglGeometrySmith(N, V, L, roughness);
-    float p5 = powf(clampf(1.0f - fmaxf(dot(H, V), 0.0f), 0.0f, 1.0f), 5.0f);
+    float p5 = spow(clampf(1.0f - fmaxf(dot(H, V), 0.0f), 0.0f, 1.0f), 5.0f);
     V3 F = F0 + (v3s(1.0f) - F0) * p5;
     V3 numerator = F * (NDF * G);
     float denominator = 4.0f * fmaxf(dot(N, V), 0.0f) * fmaxf(dot(N, L), 0.0f) + 0.0001f;
@@ -293,7 +302,7 @@ SGL_HD V4 sglFsPbr(const SglFsCtx &c, const float *v) {
   V3 ambient;
   if (uI(d, 324)) {
     float NdotV = fmaxf(dot(N, V), 0.0f);
-    float p5 = powf(clampf(1.0f - NdotV, 0.0f, 1.0f), 5.0f);
+    float p5 = spow(clampf(1.0f - NdotV, 0.0f, 1.0f), 5.0f);
     V3 F = F0 + (vmax(v3s(1.0f - roughness), F0) - F0) * p5;
     V3 kD = (v3s(1.0f) - F) * (1.0f - metallic);
     V4 irr = sglTextureCube(sglSlot(c, SGL_SLOT_PBR_IRRADIANCE), N, 0.f);
@@ -318,7 +327,7 @@ SGL_HD V4 sglFsPbr(const SglFsCtx &c, const float *v) {
 SGL_HD V4 sglFsSkybox(const SglFsCtx &c, const float *v) {
   V3 wp = v3(v[0], v[1], v[2]);
   if (c.draw->defines & SGL_DEF_EQUIRECTANGULAR_MAP) {
-    V3 dir = normalize(wp);
+    V3 dir = normalizeP(wp);   // IEEE form: this branch also performs the one-off equirect -> cube conversion
     V2 uv = v2(atan2f(dir.z, dir.x), asinf(-dir.y));
     uv = v2(uv.x * 0.1591f + 0.5f, uv.y * 0.3183f + 0.5f);
     return sglTexture2D(sglSlot(c, SGL_SLOT_SKY_EQUIRECT), uv, 0.f);   // no lodFunc installed for the skybox sampler
@@ -426,11 +435,11 @@ SGL_HD V4 sglFsFxaa(const SglFsCtx &c, const float *v) {
 // ---- ShaderIBLIrradiance::FS (IBLIrradianceSoft.h:74-104) --------------------------------------------------------
 SGL_HD V4 sglFsIrradiance(const SglFsCtx &c, const float *v) {
   SglSampler s = sglSlot(c, SGL_SLOT_IBL_CUBE);
-  V3 N = normalize(v3(v[0], v[1], v[2]));
+  V3 N = normalizeP(v3(v[0], v[1], v[2]));
   V3 irr = v3s(0.f);
   V3 up = v3(0.f, 1.f, 0.f);
-  V3 right = normalize(cross(up, N));
-  up = normalize(cross(N, right));
+  V3 right = normalizeP(cross(up, N));
+  up = normalizeP(cross(N, right));
   const float sampleDelta = 0.025f;
   float nr = 0.0f;
   for (float phi = 0.0f; phi < 2.0f * SGL_PI; phi += sampleDelta) {
@@ -439,7 +448,7 @@ SGL_HD V4 sglFsIrradiance(const SglFsCtx &c, const float *v) {
       float st = sinf(theta), ct = cosf(theta);
       V3 ts = v3(st * cp, st * sp, ct);
       V3 sv = ts.x * right + ts.y * up + ts.z * N;
-      V4 t = sglTextureCube(s, sv, 0.f);
+      V4 t = sglTextureCubeP(s, sv, 0.f);
       irr = irr + v3(t.x, t.y, t.z) * ct * st;
       nr += 1.0f;
     }
@@ -462,13 +471,13 @@ SGL_HD V4 sglFsPrefilter(const SglFsCtx &c, const float *v) {
   const SglDrawRec &d = *c.draw;
   SglSampler s = sglSlot(c, SGL_SLOT_IBL_CUBE);
   float srcRes = uF(d, 256), rough = uF(d, 260);
-  V3 N = normalize(v3(v[0], v[1], v[2]));
+  V3 N = normalizeP(v3(v[0], v[1], v[2]));
   V3 V = N;
   V3 col = v3s(0.f);
   float totalWeight = 0.f;
   float a = rough * rough;
   V3 upv = fabsf(N.z) < 0.999f ? v3(0.f, 0.f, 1.f) : v3(1.f, 0.f, 0.f);
-  V3 tangent = normalize(cross(upv, N));
+  V3 tangent = normalizeP(cross(upv, N));
   V3 bitangent = cross(N, tangent);
   for (uint32_t i = 0u; i < 1024u; ++i) {
     V2 Xi = v2((float) i / 1024.f, sglRadicalInverse(i));
@@ -476,23 +485,23 @@ SGL_HD V4 sglFsPrefilter(const SglFsCtx &c, const float *v) {
     float cosTheta = sqrtf((1.0f - Xi.y) / (1.0f + (a * a - 1.0f) * Xi.y));
     float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
     V3 Hh = v3(cosf(phi) * sinTheta, sinf(phi) * sinTheta, cosTheta);
-    V3 H = normalize(tangent * Hh.x + bitangent * Hh.y + N * Hh.z);
-    V3 L = normalize(2.0f * dot(V, H) * H - V);
+    V3 H = normalizeP(tangent * Hh.x + bitangent * Hh.y + N * Hh.z);
+    V3 L = normalizeP(2.0f * dot(V, H) * H - V);
     float NdotL = fmaxf(dot(N, L), 0.0f);
     if (NdotL > 0.0f) {
-      float D = sglDistributionGGX(N, H, rough);
+      float D = sglDistributionGGXP(N, H, rough);
       float NdotH = fmaxf(dot(N, H), 0.0f);
       float HdotV = fmaxf(dot(H, V), 0.0f);
       float pdf = D * NdotH / (4.0f * HdotV) + 0.0001f;
       float saTexel = 4.0f * SGL_PI / (6.0f * srcRes * srcRes);
       float saSample = 1.0f / (1024.f * pdf + 0.0001f);
       float mip = rough == 0.0f ? 0.0f : 0.5f * log2f(saSample / saTexel);
-      V4 t = sglTextureCube(s, L, mip);
+      V4 t = sglTextureCubeP(s, L, mip);
       col = col + v3(t.x, t.y, t.z) * NdotL;
       totalWeight += NdotL;
     }
   }
-  col = col / totalWeight;
+  col = v3(col.x / totalWeight, col.y / totalWeight, col.z / totalWeight);
   return v4(col.x, col.y, col.z, 1.0f);
 }
 

@@ -25,14 +25,15 @@ SGL_HD uint32_t sglMorton2(uint32_t x, uint32_t y) {   // MortonBuffer::encode16
   return (res | (res >> 15)) & 0xffffu;
 }
 
-SGL_HD size_t sglTexelIndex(int layout, int w, int x, int y) {
-  if (layout == SGL_LAYOUT_LINEAR) return (size_t) x + (size_t) y * (size_t) w;
+// texel index inside one level (levels are limited to 2^31 texels, checked at creation)
+SGL_HD uint32_t sglTexelIndex(int layout, int w, int x, int y) {
+  if (layout == SGL_LAYOUT_LINEAR) return (uint32_t) x + (uint32_t) y * (uint32_t) w;
   if (layout == SGL_LAYOUT_TILED) {
-    int tw = (w + 3) >> 2;
-    return (((size_t) (y >> 2) * tw + (x >> 2)) << 4) + ((y & 3) << 2) + (x & 3);
+    uint32_t tw = (uint32_t) (w + 3) >> 2;
+    return ((((uint32_t) y >> 2) * tw + ((uint32_t) x >> 2)) << 4) + (((uint32_t) y & 3u) << 2) + ((uint32_t) x & 3u);
   }
-  int tw = (w + 31) >> 5;
-  return (((size_t) (y >> 5) * tw + (x >> 5)) << 10) + sglMorton2(x & 31, y & 31);
+  uint32_t tw = (uint32_t) (w + 31) >> 5;
+  return ((((uint32_t) y >> 5) * tw + ((uint32_t) x >> 5)) << 10) + sglMorton2((uint32_t) x & 31u, (uint32_t) y & 31u);
 }
 
 SGL_HD size_t sglLevelTexels(int layout, int w, int h) {   // innerWidth * innerHeight (Buffer.h:43-48,143-148,174-179)
@@ -213,7 +214,8 @@ SGL_HDN uint32_t sglTextureImpl(const SglSampler &s, int layer, float u, float v
 }
 
 // BaseSamplerCube::convertXYZ2UV -- an if-chain where later matches override earlier ones on ties
-SGL_HD void sglCubeFace(float x, float y, float z, int &index, float &u, float &v) {
+template<bool FAST>
+SGL_HD void sglCubeFaceT(float x, float y, float z, int &index, float &u, float &v) {
   float absX = fabsf(x), absY = fabsf(y), absZ = fabsf(z);
   bool xp = x > 0, yp = y > 0, zp = z > 0;
   float maxAxis = 0.f, uc = 0.f, vc = 0.f;
@@ -225,13 +227,22 @@ SGL_HD void sglCubeFace(float x, float y, float z, int &index, float &u, float &
   if (zp && absZ >= absX && absZ >= absY) { maxAxis = absZ; uc = x; vc = y; index = 4; }
   if (!zp && absZ >= absX && absZ >= absY) { maxAxis = absZ; uc = -x; vc = y; index = 5; }
   vc = -vc;
-  u = 0.5f * (uc / maxAxis + 1.0f);
-  v = 0.5f * (vc / maxAxis + 1.0f);
+  u = 0.5f * ((FAST ? sdiv(uc, maxAxis) : uc / maxAxis) + 1.0f);
+  v = 0.5f * ((FAST ? sdiv(vc, maxAxis) : vc / maxAxis) + 1.0f);
 }
+SGL_HD void sglCubeFace(float x, float y, float z, int &index, float &u, float &v) { sglCubeFaceT<false>(x, y, z, index, u, v); }
 
+// float(c) / 255.f for c in 0..255, bit-exact without an IEEE division: with r = RN(1/255), q0 = RN(c*r),
+// RN(q0 + r * (c - 255*q0)) is the correctly rounded quotient (Markstein); checked exhaustively for all 256 inputs
+// (tests/test_capi_and_host.py::test_div255_identity)
+SGL_HD float sglDiv255(float c) {
+  const float r = 1.0f / 255.0f;
+  float q0 = xmul(c, r);
+  return xfma(xfma(-q0, 255.0f, c), r, q0);
+}
 SGL_HD V4 sglUnpackRGBA(uint32_t p) {   // vec4(u8vec4) / 255.f   (ShaderSoft.h:80-111)
-  return v4((float) (p & 0xffu) / 255.f, (float) ((p >> 8) & 0xffu) / 255.f, (float) ((p >> 16) & 0xffu) / 255.f,
-            (float) (p >> 24) / 255.f);
+  return v4(sglDiv255((float) (p & 0xffu)), sglDiv255((float) ((p >> 8) & 0xffu)), sglDiv255((float) ((p >> 16) & 0xffu)),
+            sglDiv255((float) (p >> 24)));
 }
 
 SGL_HD V4 sglTexture2D(const SglSampler &s, V2 uv, float lod) {
@@ -243,10 +254,14 @@ SGL_HD V4 sglTexture2DOffset(const SglSampler &s, V2 uv, float lod, int ox, int 
 SGL_HD float sglTexture2DFloat(const SglSampler &s, V2 uv) {
   return sglBitsFloat(sglTextureImpl(s, 0, uv.x, uv.y, 0.f, 0, 0));
 }
-SGL_HD V4 sglTextureCube(const SglSampler &s, V3 dir, float lod) {
+template<bool FAST>
+SGL_HD V4 sglTextureCubeT(const SglSampler &s, V3 dir, float lod) {
   int face;
   float u, v;
-  sglCubeFace(dir.x, dir.y, dir.z, face, u, v);
+  sglCubeFaceT<FAST>(dir.x, dir.y, dir.z, face, u, v);
   if (s.tex == nullptr || face >= s.tex->layers) return v4(0, 0, 0, 0);
   return sglUnpackRGBA(sglTextureImpl(s, face, u, v, lod, 0, 0));
 }
+// per-frame shaders (PBR, skybox) take the SFU division for the face coordinates; IBL generation keeps IEEE arithmetic
+SGL_HD V4 sglTextureCube(const SglSampler &s, V3 dir, float lod) { return sglTextureCubeT<true>(s, dir, lod); }
+SGL_HD V4 sglTextureCubeP(const SglSampler &s, V3 dir, float lod) { return sglTextureCubeT<false>(s, dir, lod); }

@@ -257,7 +257,36 @@ int sgl_pass_end(void) {
   P.clearColor = c; P.clearDepth = clearDepth;
   P.draws = draws.data(); P.drawCount = nDraws; P.prims = prims.data(); P.primVerts = pverts.data(); P.primKeys = keys.data(); P.primSlots = primSlots;
   P.textures = texTable.data();
-  if (getenv("SGLEMU_VERBOSE")) fprintf(stderr, "[emu] pass %dx%d s%d draws %d prims %zu\n", fbW, fbH, samples, nDraws, order.size());
+  if (getenv("SGLEMU_VERBOSE")) {
+    fprintf(stderr, "[emu] pass %dx%d s%d draws %d prims %zu\n", fbW, fbH, samples, nDraws, order.size());
+    int tX = (fbW + SGL_TILE - 1) / SGL_TILE, tY = (fbH + SGL_TILE - 1) / SGL_TILE;
+    std::vector<int> cnt(tX * tY, 0), cntBox(tX * tY, 0);
+    long long big = 0;
+    for (uint32_t slot : order) {
+      const SglPrim &p = prims[slot];
+      int x0 = std::max<int>(p.bx0, 0), y0 = std::max<int>(p.by0, 0), x1 = std::min<int>(p.bx1, fbW - 1), y1 = std::min<int>(p.by1, fbH - 1);
+      if (x1 < x0 || y1 < y0) continue;
+      int n = (x1 / SGL_TILE - x0 / SGL_TILE + 1) * (y1 / SGL_TILE - y0 / SGL_TILE + 1);
+      if (n > SGL_BIG_PRIM_TILES) big++;
+      for (int ty = y0 / SGL_TILE; ty <= y1 / SGL_TILE; ty++)
+        for (int tx = x0 / SGL_TILE; tx <= x1 / SGL_TILE; tx++) {
+          cntBox[ty * tX + tx]++;
+          bool near = true;
+          if ((p.flags & SGL_PF_KIND_MASK) == SGL_PK_TRIANGLE) {
+            SglTriEdge e = sglTriEdge(p);
+            near = !sglTriSurelyOutside(e, tx * SGL_TILE + 8.f, ty * SGL_TILE + 8.f, 8.f, 8.f);
+          } else if ((p.flags & SGL_PF_KIND_MASK) == SGL_PK_LINE) near = sglLineNearRect(p, tx * SGL_TILE, ty * SGL_TILE, tx * SGL_TILE + 15, ty * SGL_TILE + 15);
+          if (near) cnt[ty * tX + tx]++;
+        }
+    }
+    auto stats = [&](std::vector<int> v, const char *nm) {
+      std::sort(v.begin(), v.end());
+      long long sum = 0; for (int c : v) sum += c;
+      fprintf(stderr, "[emu]   %s per tile: sum %lld mean %.1f p50 %d p90 %d p99 %d max %d  (tiles %zu, big prims %lld)\n", nm, sum, (double) sum / v.size(),
+              v[v.size() / 2], v[v.size() * 9 / 10], v[v.size() * 99 / 100], v.back(), v.size(), big);
+    };
+    stats(cntBox, "bbox "); stats(cnt, "culled");
+  }
   if (samples == 4) rasterAll<4>(P, order); else rasterAll<1>(P, order);
   draws.clear();
   return 0;
