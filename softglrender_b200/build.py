@@ -13,8 +13,8 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
-CU_SOURCES = ["sglcuda.cu", "sgl_raster_ns1.cu", "sgl_raster_ns4.cu", "sgl_vis.cu", "sgl_shade_ns1.cu", "sgl_shade_ns4.cu"]
-HEADERS = ["sgl_kernels.cuh", "sgl_vis.cuh", "sgl_pixel.h", "sgl_setup.h", "sgl_raster.h", "sgl_shaders.h", "sgl_texture.h",
+CU_SOURCES = ["sglcuda.cu", "sgl_raster_ns1.cu", "sgl_raster_ns4.cu", "sgl_vis.cu", "sgl_depth.cu", "sgl_shade_ns1.cu", "sgl_shade_ns4.cu"]
+HEADERS = ["sgl_kernels.cuh", "sgl_vis.cuh", "sgl_depth.cuh", "sgl_pixel.h", "sgl_setup.h", "sgl_raster.h", "sgl_shaders.h", "sgl_texture.h",
            "sgl_math.h", "sgl_types.h", os.path.join(ROOT, "include", "sglcuda.h")]
 
 

@@ -33,6 +33,8 @@ __device__ __forceinline__ bool sglPrimTiles(const SglPrim &p, int fbW, int fbH,
 }
 
 struct SglDeviceAlloc {
+  static constexpr bool kRecords = true;
+  __device__ void consume(const SglDrawRec &, const SglPrim &) {}
   SglSetupShared S;
   __device__ int newVertex(const SglDrawRec &d) {
     int extra = atomicAdd(d.vertexCounter, 1);

@@ -25,25 +25,28 @@ SGL_HD void sglStoreV4(float *base, int i, V4 v) {
 }
 
 // vertexShaderImpl + perspective divide + viewport for vertex slot `idx` whose attributes are at `attr`
-SGL_HD void sglProcessVertex(const SglDrawRec &d, int idx, const float *attr) {
+SGL_HD V4 sglProcessVertex(const SglDrawRec &d, int idx, const float *attr) {
   float vary[32];
   V4 clip = sglVertexShader(d, attr, vary);
   for (int k = 0; k < d.varyingStride; k++) d.varyings[(size_t) idx * d.varyingStride + k] = vary[k];
   sglStoreV4(d.clipPos, idx, clip);
   d.clipMask[idx] = sglClipMask(clip);
   sglStoreV4(d.fragPos, idx, sglToScreen(clip, d.vpX, d.vpY, d.vpW, d.vpH));
+  return clip;
 }
 
 // clippingNewVertex: VS(mix(attributes of idx0, idx1, t)); returns the new index or -1 when the arena is full
 template<class Alloc>
-SGL_HD int sglClipNewVertex(const SglDrawRec &d, Alloc &alloc, int idx0, int idx1, float t) {
+SGL_HD int sglClipNewVertex(const SglDrawRec &d, Alloc &alloc, int idx0, int idx1, float t, V4 *clipOut = nullptr) {
   int idx = alloc.newVertex(d);
   if (idx < 0) return -1;
   const float *a0 = sglAttrPtr(d, idx0), *a1 = sglAttrPtr(d, idx1);
   float *out = d.vertexOut + (size_t) (idx - d.vertexCount) * 16;
   float omt = xsub(1.f, t);
-  for (int k = 0; k < 16; k++) out[k] = xMix(a0[k], a1[k], t, omt);
-  sglProcessVertex(d, idx, out);
+  float attr[16];
+  for (int k = 0; k < 16; k++) attr[k] = out[k] = xMix(a0[k], a1[k], t, omt);
+  V4 clip = sglProcessVertex(d, idx, attr);
+  if (clipOut) *clipOut = clip;
   return idx;
 }
 
@@ -55,30 +58,38 @@ SGL_HD int sglClipTriangle(const SglDrawRec &d, Alloc &alloc, int i0, int i1, in
   poly[0] = i0; poly[1] = i1; poly[2] = i2;
   if (mask == 0) return 3;
   int in[12], out[12];
+  V4 cin[12], cout[12];          // clip positions of the working polygon (no store -> load round trips through memory)
   int nin = 3, nout = 0;
   in[0] = i0; in[1] = i1; in[2] = i2;
+  cin[0] = sglLoadV4(d.clipPos, i0); cin[1] = sglLoadV4(d.clipPos, i1); cin[2] = sglLoadV4(d.clipPos, i2);
   for (int plane = 0; plane < 6; plane++) {
     if (!(mask & (1 << plane))) continue;
     if (nin < 3) return 0;                       // fullClip
     nout = 0;
     int idxPre = in[0];
-    float dPre = sglPlaneDist(plane, sglLoadV4(d.clipPos, idxPre));
+    V4 cPre = cin[0];
+    float dPre = sglPlaneDist(plane, cPre);
     in[nin] = idxPre;
+    cin[nin] = cPre;
     for (int i = 1; i <= nin; i++) {
       int idx = in[i];
-      float dd = sglPlaneDist(plane, sglLoadV4(d.clipPos, idx));
-      if (dPre >= 0) out[nout++] = idxPre;
+      V4 cc = cin[i];
+      float dd = sglPlaneDist(plane, cc);
+      if (dPre >= 0) { out[nout] = idxPre; cout[nout++] = cPre; }
       if (sglSignBit(dPre) != sglSignBit(dd)) {
         float t = dd < 0 ? xdiv(dPre, xsub(dPre, dd)) : xdiv(-dPre, xsub(dd, dPre));
-        int nv = sglClipNewVertex(d, alloc, idxPre, idx, t);
+        V4 cn;
+        int nv = sglClipNewVertex(d, alloc, idxPre, idx, t, &cn);
         if (nv < 0) return -1;
-        out[nout++] = nv;
+        out[nout] = nv;
+        cout[nout++] = cn;
       }
       idxPre = idx;
+      cPre = cc;
       dPre = dd;
     }
     nin = nout;
-    for (int i = 0; i < nout; i++) in[i] = out[i];
+    for (int i = 0; i < nout; i++) { in[i] = out[i]; cin[i] = cout[i]; }
   }
   if (nin < 3) return 0;
   for (int i = 0; i < nin; i++) poly[i] = in[i];
@@ -212,6 +223,7 @@ SGL_HD bool sglSetupLine(SglPrim &p, V4 f0, V4 f1, float width, uint32_t stateFl
 template<class Alloc>
 SGL_HD void sglEmitPrim(const SglSetupOut &o, Alloc &alloc, const SglDrawRec &d, int slot, uint32_t key, const SglPrim &p,
                         int i0, int i1, int i2) {
+  if (!Alloc::kRecords) { alloc.consume(d, p); return; }   // immediate-mode consumers (depth-only atomic path)
   o.prims[slot] = p;
   SglPrimVerts pv = {(uint32_t) i0, (uint32_t) i1, (uint32_t) i2, 0u};
   o.primVerts[slot] = pv;
@@ -230,7 +242,7 @@ SGL_HD void sglProcessInputPrim(const SglDrawRec &d, uint32_t drawIdx, int i, bo
   const int baseSlot = d.primBase + i * d.slotsPerPrim;
   const uint32_t baseKey = (uint32_t) d.keyBase + (uint32_t) (i * d.slotsPerPrim);
   // invalidate this input primitive's original slots first
-  for (int e = 0; e < d.slotsPerPrim; e++) {
+  for (int e = 0; Alloc::kRecords && e < d.slotsPerPrim; e++) {
     o.prims[baseSlot + e].flags = 0;
     o.primKeys[baseSlot + e] = baseKey + e;
   }
@@ -265,7 +277,7 @@ SGL_HD void sglProcessInputPrim(const SglDrawRec &d, uint32_t drawIdx, int i, bo
       bool front = sglFrontFacing(fa, fb, fc);
       int slot = k == 0 ? baseSlot : appendSlot + (k - 1);
       uint32_t key = k == 0 ? baseKey : (uint32_t) d.keyBase + (uint32_t) (d.inputPrims * d.slotsPerPrim) + (uint32_t) (6 * i + (k - 1));
-      if (k > 0) { o.prims[slot].flags = 0; o.primKeys[slot] = key; }
+      if (Alloc::kRecords && k > 0) { o.prims[slot].flags = 0; o.primKeys[slot] = key; }
       if (rs.cull_face && !front) continue;
       if (sglSetupTriangle(p, fa, fb, fc, d.vpW, d.vpH, front, sf, drawIdx)) sglEmitPrim(o, alloc, d, slot, key, p, a, b, c);
     }

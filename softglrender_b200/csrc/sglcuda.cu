@@ -20,6 +20,9 @@ extern "C" int sglLaunchRaster4(const SglPassParams *P, int nTiles, void *stream
 extern "C" int sglLaunchVis(int samples, const SglPassParams *P, int nTiles, void *stream);
 extern "C" int sglLaunchShade1(const SglPassParams *P, int nTiles, void *stream);
 extern "C" int sglLaunchShade4(const SglPassParams *P, int nTiles, void *stream);
+// depth-only passes (sgl_depth.cu)
+#include "sgl_depth_pass.h"
+extern "C" int sglLaunchDepthOnly(int samples, const SglDepthPass *D, int maxPrims, int nDraws, int nTiles, void *stream);
 
 namespace {
 
@@ -707,6 +710,19 @@ int sgl_pass_end(void) {
   const int nTiles = tilesX * tilesY;
   const int nDraws = (int) g.draws.size();
 
+  // Depth-only passes whose result is order independent (filled triangles, depth test + write on, one direction of
+  // depth function) skip binning entirely: prim-parallel setup with atomicMin/Max rasterisation (sgl_depth.cuh).
+  bool depthOnly = !g.forceFused && !ct && dt && nDraws > 0;
+  int dir = 0;
+  for (int i = 0; i < nDraws && depthOnly; i++) {
+    const SglRenderStates &rs = g.draws[i].rs;
+    int f = rs.depth_func;
+    int d = (f == 1 || f == 3) ? 1 : ((f == 4 || f == 6) ? 2 : 0);
+    if (rs.primitive_type != SGL_PRIM_TRIANGLE || rs.polygon_mode != SGL_POLY_FILL || !rs.depth_test || !rs.depth_mask || d == 0 ||
+        (dir != 0 && d != dir))
+      depthOnly = false;
+    dir = d;
+  }
   // ---- arena layout
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = alignUp(off + bytes, 256); return o; };
@@ -754,6 +770,8 @@ int sgl_pass_end(void) {
   size_t oPrimKeys = take(sizeof(uint32_t) * std::max(primSlots, 1));
   size_t oBigList = take(sizeof(uint32_t) * std::max(primSlots, 1));
   size_t binCapacity = std::min<size_t>(std::max<size_t>((size_t) primSlots * 8, 1 << 20), (size_t) 1 << 29);
+  // depth-only path: the region holds 64-byte work items instead (>= 2 per primitive slot + one per 512 framebuffer pixels)
+  if (depthOnly) binCapacity = ((size_t) primSlots * 2 + (size_t) fbW * fbH / 512 + 65536) * (sizeof(SglPrim) / sizeof(uint32_t));
   size_t oBins = take(sizeof(uint32_t) * binCapacity);
   int rc = ensureArena(off);
   if (rc) return rc;
@@ -814,6 +832,48 @@ int sgl_pass_end(void) {
   P.bigCapacity = (uint32_t) std::max(primSlots, 1);
   P.textures = g.dTextures;
   P.counters = g.dCounters;
+
+  if (depthOnly) {
+    if (maxVerts > 0) {
+      rc = launch("sglVertexKernel", sglVertexKernel, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws);
+      if (rc) return rc;
+    }
+    if (g.clearDepthFlag) {
+      uint32_t bits;
+      memcpy(&bits, &g.clearDepth, 4);
+      size_t n = (size_t) fbW * fbH * samples;
+      rc = launch("sglFill32Kernel", sglFill32Kernel, dim3((unsigned) std::min<size_t>((n + 1023) / 1024, 148 * 8)), dim3(256), (uint32_t *) P.depthBase, bits, n);
+      if (rc) return rc;
+    }
+    SglDepthPass D;
+    memset(&D, 0, sizeof(D));
+    D.draws = P.draws;
+    D.depthBase = P.depthBase;
+    D.fbW = fbW; D.fbH = fbH;
+    D.useMin = dir == 1;
+    // work queue in the bin region (4 bytes x binCapacity), huge-triangle queue in the primitive-record region
+    D.queue = (SglPrim *) (A + oBins);
+    D.queueCount = P.bigCount;
+    D.queueCapacity = (uint32_t) (binCapacity * sizeof(uint32_t) / sizeof(SglPrim));
+    D.large = (SglPrim *) (A + oPrims);
+    D.largeCount = P.tileCount;          // zero-initialised with the rest of the counter block
+    D.largeCapacity = (uint32_t) std::max(primSlots, 1);
+    D.counters = g.dCounters;
+    D.tileOwner = P.tileOwner;
+    D.tilesX = tilesX;
+    D.rank = g.rank;
+    if (maxPrims > 0) {
+      profBegin(samples == 4 ? "sglDepthOnly<4>" : "sglDepthOnly<1>");
+      int e = sglLaunchDepthOnly(samples, &D, maxPrims, nDraws, nTiles, (void *) g.stream);
+      profEnd();
+      g.hostLaunches += 3;
+      if (e != 0) return fail(SGL_ERR_CUDA, "depth-only kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
+    }
+    g.hostPasses++;
+    g.hostDraws += nDraws;
+    g.draws.clear();
+    return SGL_OK;
+  }
 
   if (nDraws) {
     if (maxVerts > 0) {

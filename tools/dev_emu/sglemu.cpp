@@ -26,6 +26,8 @@ std::string err;
 unsigned long long overflowCount = 0;
 
 struct HostAlloc {
+  static constexpr bool kRecords = true;
+  void consume(const SglDrawRec &, const SglPrim &) {}
   std::vector<int> *vc, *ac;
   int newVertex(const SglDrawRec &d) { int e = (*d.vertexCounter)++; int i = d.vertexCount + e; return i < d.vertexCap ? i : -1; }
   int newAppendSlots(const SglDrawRec &d, int n) { int a = *d.appendCounter; *d.appendCounter += n; return a + n <= d.appendCap ? d.appendBase + a : -1; }
@@ -286,6 +288,20 @@ int sgl_pass_end(void) {
               v[v.size() / 2], v[v.size() * 9 / 10], v[v.size() * 99 / 100], v.back(), v.size(), big);
     };
     stats(cntBox, "bbox "); stats(cnt, "culled");
+    {
+      std::vector<int> areas;
+      for (uint32_t slot : order) {
+        const SglPrim &p = prims[slot];
+        int x0 = std::max<int>(p.bx0, 0), y0 = std::max<int>(p.by0, 0), x1 = std::min<int>(p.bx1, fbW - 1), y1 = std::min<int>(p.by1, fbH - 1);
+        if (x1 >= x0 && y1 >= y0) areas.push_back((x1 - x0 + 1) * (y1 - y0 + 1));
+      }
+      std::sort(areas.begin(), areas.end());
+      long long sum = 0; for (int a : areas) sum += a;
+      int c256 = 0, c4096 = 0, c64k = 0;
+      for (int a : areas) { c256 += a > 256; c4096 += a > 4096; c64k += a > 65536; }
+      if (!areas.empty()) fprintf(stderr, "[emu]   pixel-range area: n %zu sum %lld p50 %d p90 %d p99 %d max %d  >256: %d >4096: %d >65536: %d\n", areas.size(), sum,
+              areas[areas.size() / 2], areas[areas.size() * 9 / 10], areas[areas.size() * 99 / 100], areas.back(), c256, c4096, c64k);
+    }
   }
   if (samples == 4) rasterAll<4>(P, order); else rasterAll<1>(P, order);
   draws.clear();
