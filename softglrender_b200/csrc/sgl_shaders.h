@@ -122,7 +122,7 @@ SGL_HD V4 sglVertexShader(const SglDrawRec &d, const float *vin, float *vout) {
 // ---- fragment shader context -----------------------------------------------------------------------------
 struct SglFsCtx {
   const SglDrawRec *draw;
-  const SglTexObj *textures;
+  const SglTexObj *textures;   // device texture table; entry 0 is a 1x1 dummy texture (unbound maps of the fast paths)
   // texture coordinates of quad pixels p0, p1, p2 (DerivativeContext, ShaderSoft.h:20-25); valid only when a
   // mip-filtered 2D sampler is bound
   bool derivValid;
@@ -323,6 +323,136 @@ SGL_HD V4 sglFsPbr(const SglFsCtx &c, const float *v) {
   return v4(color.x, color.y, color.z, albedoRgba.w);
 }
 
+
+// ---- ShaderPbrIBL::FS, straight-line form for "simple" samplers ------------------------------------------------
+// Same expressions as sglFsPbr in the same order; the only difference is that the texel loads of all material maps
+// are issued before the first use (and unbound maps read a 1x1 dummy texture instead of branching), which turns seven
+// dependent memory round trips per pixel into two.
+SGL_HD SglTapView sglSlotTapView(const SglFsCtx &c, int slot, bool enabled, int layer, int level) {
+  const SglSamplerSlot &b = c.draw->samplers[slot];
+  const SglTexObj *t = &c.textures[enabled ? b.tex : 0];
+  return sglTapView(t, enabled ? layer : 0, enabled ? level : 0, enabled ? b.wrap : SGL_WRAP_CLAMP_TO_EDGE);
+}
+
+SGL_HD V4 sglFsPbrFast(const SglFsCtx &c, const float *v) {
+  const SglDrawRec &d = *c.draw;
+  V2 uv = v2(v[0], v[1]);
+  const bool hasAlbedo = (d.defines & SGL_DEF_ALBEDO_MAP) != 0, hasNormal = (d.defines & SGL_DEF_NORMAL_MAP) != 0;
+  const bool hasEmissive = (d.defines & SGL_DEF_EMISSIVE_MAP) != 0, hasAo = (d.defines & SGL_DEF_AO_MAP) != 0;
+  const bool hasMr = (d.defines & SGL_DEF_METALROUGHNESS_MAP) != 0;
+  SglTap tAlbedo = sglTapIssue(sglSlotTapView(c, SGL_SLOT_ALBEDO, hasAlbedo, 0, 0), uv.x, uv.y);
+  SglTap tMr = sglTapIssue(sglSlotTapView(c, SGL_SLOT_PBR_METALROUGH, hasMr, 0, 0), uv.x, uv.y);
+  SglTap tAo = sglTapIssue(sglSlotTapView(c, SGL_SLOT_AO, hasAo, 0, 0), uv.x, uv.y);
+  SglTap tNormal = sglTapIssue(sglSlotTapView(c, SGL_SLOT_NORMAL, hasNormal, 0, 0), uv.x, uv.y);
+  SglTap tEmissive = sglTapIssue(sglSlotTapView(c, SGL_SLOT_EMISSIVE, hasEmissive, 0, 0), uv.x, uv.y);
+
+  V4 albedoRgba = hasAlbedo ? sglUnpackRGBA(sglTapMix(tAlbedo)) : uV4(d, 352);
+  V3 albedo = vpow(v3(albedoRgba.x, albedoRgba.y, albedoRgba.z), 2.2f);
+  float metallic = 0.0f, roughness = 1.0f;
+  {
+    V4 mr = sglUnpackRGBA(sglTapMix(tMr));
+    metallic = hasMr ? mr.z : metallic;
+    roughness = hasMr ? mr.y : roughness;
+  }
+  float ao = hasAo ? sglUnpackRGBA(sglTapMix(tAo)).x : 1.f;
+  V3 N;
+  {
+    V3 Nn = normalize(v3(v[20], v[21], v[22]));
+    V3 T = normalize(v3(v[24], v[25], v[26]));
+    T = normalize(T - dot(T, Nn) * Nn);
+    V3 B = cross(T, Nn);
+    V4 t = sglUnpackRGBA(sglTapMix(tNormal));
+    V3 tn = v3(t.x * 2.0f - 1.0f, t.y * 2.0f - 1.0f, t.z * 2.0f - 1.0f);
+    V3 mapped = normalize(T * tn.x + B * tn.y + Nn * tn.z);
+    V3 plain = normalize(v3(v[4], v[5], v[6]));
+    N = hasNormal ? mapped : plain;
+  }
+  V3 V = normalize(v3(v[12], v[13], v[14]));
+  V3 R = reflect(-V, N);
+  // IBL taps (irradiance: level 0; prefilter: two levels around roughness * 4), issued as soon as N, R and roughness exist
+  const bool ibl = uI(d, 324) != 0;
+  SglTap tIrr, tPreHi, tPreLo;
+  float preFr = 0.f;
+  bool preSame = true;
+  {
+    int face;
+    float fu, fv;
+    sglCubeFaceT<true>(N.x, N.y, N.z, face, fu, fv);
+    tIrr = sglTapIssue(sglSlotTapView(c, SGL_SLOT_PBR_IRRADIANCE, ibl, face, 0), fu, fv);
+    sglCubeFaceT<true>(R.x, R.y, R.z, face, fu, fv);
+    const SglSamplerSlot &b = d.samplers[SGL_SLOT_PBR_PREFILTER];
+    const SglTexObj *t = &c.textures[ibl ? b.tex : 0];
+    float lod = roughness * 4.0f;
+    int maxLevel = (ibl && b.filter == SGL_FILTER_LINEAR_MIPMAP_LINEAR) ? t->levels - 1 : 0;
+    int hi = (int) floorf(lod);
+    hi = hi < 0 ? 0 : (hi > maxLevel ? maxLevel : hi);
+    int lo = hi + 1;
+    lo = lo > maxLevel ? maxLevel : lo;
+    preSame = hi == lo;
+    preFr = xsub(lod, floorf(lod));
+    tPreHi = sglTapIssue(sglSlotTapView(c, SGL_SLOT_PBR_PREFILTER, ibl, face, hi), fu, fv);
+    tPreLo = sglTapIssue(sglSlotTapView(c, SGL_SLOT_PBR_PREFILTER, ibl, face, lo), fu, fv);
+  }
+  V3 F0 = vmix(v3s(0.04f), albedo, metallic);
+  V3 Lo = v3s(0.0f);
+  V3 lightVec = v3(v[16], v[17], v[18]);
+  if (uI(d, 320)) {
+    V3 L = normalize(lightVec);
+    V3 H = normalize(V + L);
+    V3 lDir = lightVec * (1.0f / 5.f);
+    float atten = clampf(1.0f - dot(lDir, lDir), 0.0f, 1.0f);
+    V3 radiance = uV3(d, 304) * atten;
+    float NDF = sglDistributionGGX(N, H, roughness);
+    float G = sglGeometrySmith(N, V, L, roughness);
+    float p5 = spow(clampf(1.0f - fmaxf(dot(H, V), 0.0f), 0.0f, 1.0f), 5.0f);
+    V3 F = F0 + (v3s(1.0f) - F0) * p5;
+    V3 numerator = F * (NDF * G);
+    float denominator = 4.0f * fmaxf(dot(N, V), 0.0f) * fmaxf(dot(N, L), 0.0f) + 0.0001f;
+    V3 specular = numerator / denominator;
+    V3 kD = (v3s(1.0f) - F) * (1.0f - metallic);
+    float NdotL = fmaxf(dot(N, L), 0.0f);
+    Lo = Lo + (kD * albedo / SGL_PI + specular) * radiance * NdotL;
+  }
+  V3 ambient;
+  if (ibl) {
+    float NdotV = fmaxf(dot(N, V), 0.0f);
+    float p5 = spow(clampf(1.0f - NdotV, 0.0f, 1.0f), 5.0f);
+    V3 F = F0 + (vmax(v3s(1.0f - roughness), F0) - F0) * p5;
+    V3 kD = (v3s(1.0f) - F) * (1.0f - metallic);
+    V4 irr = sglUnpackRGBA(sglTapMix(tIrr));
+    V3 diffuse = v3(irr.x, irr.y, irr.z) * albedo;
+    uint32_t pHi = sglTapMix(tPreHi), pLo = sglTapMix(tPreLo);
+    V4 pre = sglUnpackRGBA(preSame ? pHi : sglMixTexel(SGL_FMT_RGBA8, pHi, pLo, preFr));
+    V3 specular = v3(pre.x, pre.y, pre.z) * sglEnvBRDFApprox(F, roughness, NdotV);
+    ambient = (kD * diffuse + specular) * ao;
+  } else {
+    ambient = uV3(d, 256) * albedo * ao;
+  }
+  V3 color = vpow(ambient + Lo, 1.0f / 2.2f);
+  V4 e = sglUnpackRGBA(sglTapMix(tEmissive));
+  V3 emissive = hasEmissive ? v3(e.x, e.y, e.z) : v3s(0.f);
+  color = color + emissive;
+  return v4(color.x, color.y, color.z, albedoRgba.w);
+}
+
+// host side of SglDrawRec::fastSamplers: is sampler slot `slot` of program `shader`, bound to texture t, "simple"?
+SGL_HD bool sglSamplerIsSimple(int shader, int slot, const SglTexObj &t, int filter, int wrap) {
+  if (t.base == nullptr || t.format != SGL_FMT_RGBA8 || t.samples != 1 || t.layout != SGL_LAYOUT_LINEAR) return false;
+  if (wrap != SGL_WRAP_REPEAT && wrap != SGL_WRAP_CLAMP_TO_EDGE) return false;
+  const bool cubeSlot = shader == SGL_SHADER_PBR && (slot == SGL_SLOT_PBR_IRRADIANCE || slot == SGL_SLOT_PBR_PREFILTER);
+  if (t.layers != (cubeSlot ? 6 : 1)) return false;
+  if (filter == SGL_FILTER_LINEAR) return true;
+  return shader == SGL_SHADER_PBR && slot == SGL_SLOT_PBR_PREFILTER && filter == SGL_FILTER_LINEAR_MIPMAP_LINEAR;
+}
+
+// true when every sampler the PBR program is going to use for this draw is "simple" (SglDrawRec::fastSamplers)
+SGL_HD bool sglPbrFastEligible(const SglDrawRec &d) {
+  uint32_t need = d.defines & 0x1fu;
+  if (uI(d, 324)) need |= (1u << SGL_SLOT_PBR_IRRADIANCE) | (1u << SGL_SLOT_PBR_PREFILTER);
+  // slot order == define order for the five material maps except metalRoughness (define bit 4 -> slot 4): identical
+  return (d.fastSamplers & need) == need;
+}
+
 // ---- ShaderSkybox::FS (SkyboxSoft.h:79-98) --------------------------------------------------------------------
 SGL_HD V4 sglFsSkybox(const SglFsCtx &c, const float *v) {
   V3 wp = v3(v[0], v[1], v[2]);
@@ -510,7 +640,7 @@ SGL_HD V4 sglFragmentShader(const SglFsCtx &c, const float *varyings) {
   switch (c.draw->shader) {
     case SGL_SHADER_BASIC: return uV4(*c.draw, 288);          // BasicSoft.h:76-78: FragColor = u_baseColor
     case SGL_SHADER_BLINNPHONG: return sglFsBlinnPhong(c, varyings);
-    case SGL_SHADER_PBR: return sglFsPbr(c, varyings);
+    case SGL_SHADER_PBR: return sglPbrFastEligible(*c.draw) ? sglFsPbrFast(c, varyings) : sglFsPbr(c, varyings);
     case SGL_SHADER_SKYBOX: return sglFsSkybox(c, varyings);
     case SGL_SHADER_FXAA: return sglFsFxaa(c, varyings);
     case SGL_SHADER_IBL_IRRADIANCE: return sglFsIrradiance(c, varyings);

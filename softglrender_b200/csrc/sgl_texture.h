@@ -265,3 +265,54 @@ SGL_HD V4 sglTextureCubeT(const SglSampler &s, V3 dir, float lod) {
 // per-frame shaders (PBR, skybox) take the SFU division for the face coordinates; IBL generation keeps IEEE arithmetic
 SGL_HD V4 sglTextureCube(const SglSampler &s, V3 dir, float lod) { return sglTextureCubeT<true>(s, dir, lod); }
 SGL_HD V4 sglTextureCubeP(const SglSampler &s, V3 dir, float lod) { return sglTextureCubeT<false>(s, dir, lod); }
+
+// ---- split-phase bilinear taps for the straight-line shader fast paths ----------------------------------------
+// A "simple" sampler = RGBA8, one sample, LINEAR layout, wrap REPEAT or CLAMP_TO_EDGE (checked per draw on the host,
+// SglDrawRec::fastSamplers).  sglTapIssue computes the footprint exactly like sampleBilinear/samplePixelBilinear and
+// issues the four texel loads without consuming them, so that a shader can put the loads of all its maps in flight
+// before the first truncating mix; sglTapMix then performs the reference's three u8 mixes.  Same arithmetic, same bits.
+struct SglTapView {
+  const uint32_t *ptr;   // level base
+  int w, h;
+  bool clamp;            // CLAMP_TO_EDGE, else REPEAT
+};
+struct SglTap {
+  uint32_t s1, s2, s3, s4;
+  float fx, fy;
+};
+SGL_HD SglTapView sglTapView(const SglTexObj *t, int layer, int level, int wrap) {
+  SglTapView v;
+  v.w = sglLevelDim(t->width, level);
+  v.h = sglLevelDim(t->height, level);
+  v.ptr = (const uint32_t *) (t->base + (size_t) layer * t->layerStride + t->levelOffset[level]);
+  v.clamp = wrap == SGL_WRAP_CLAMP_TO_EDGE;
+  return v;
+}
+SGL_HD SglTapView sglTapViewDummy(const uint32_t *dummy) {
+  SglTapView v;
+  v.ptr = dummy; v.w = 1; v.h = 1; v.clamp = true;
+  return v;
+}
+SGL_HD int sglTapWrap(int x, int n, bool clamp) {
+  int r = (x & ((n - 1) + n)) & (n - 1);                 // CoordMod (SamplerSoft.h:14)
+  int c = x < 0 ? 0 : (x >= n ? n - 1 : x);
+  return clamp ? c : r;
+}
+SGL_HD SglTap sglTapIssue(const SglTapView &t, float u, float v) {   // uv normalised
+  float tu = xsub(xadd(xmul(u, (float) t.w), 0.f), 0.5f), tv = xsub(xadd(xmul(v, (float) t.h), 0.f), 0.5f);
+  float fu = floorf(tu), fv = floorf(tv);
+  int x0 = (int) fu, y0 = (int) fv;
+  int xa = sglTapWrap(x0, t.w, t.clamp), xb = sglTapWrap(x0 + 1, t.w, t.clamp);
+  int ya = sglTapWrap(y0, t.h, t.clamp), yb = sglTapWrap(y0 + 1, t.h, t.clamp);
+  SglTap r;
+  r.s1 = SGL_LDG(t.ptr + (uint32_t) ya * (uint32_t) t.w + (uint32_t) xa);
+  r.s2 = SGL_LDG(t.ptr + (uint32_t) ya * (uint32_t) t.w + (uint32_t) xb);
+  r.s3 = SGL_LDG(t.ptr + (uint32_t) yb * (uint32_t) t.w + (uint32_t) xa);
+  r.s4 = SGL_LDG(t.ptr + (uint32_t) yb * (uint32_t) t.w + (uint32_t) xb);
+  r.fx = xsub(tu, fu);
+  r.fy = xsub(tv, fv);
+  return r;
+}
+SGL_HD uint32_t sglTapMix(const SglTap &a) {
+  return sglMixTexel(SGL_FMT_RGBA8, sglMixTexel(SGL_FMT_RGBA8, a.s1, a.s2, a.fx), sglMixTexel(SGL_FMT_RGBA8, a.s3, a.s4, a.fx), a.fy);
+}

@@ -87,7 +87,9 @@ struct __attribute__((aligned(16))) SglDrawRec {
   int32_t keyBase;                        // pass-global order key of slot 0
   int32_t hasColor;
   float pointSize;
-  int32_t pad[3];
+  uint32_t fastSamplers;                  // bit s: sampler slot s is "simple" (sgl_texture.h split-phase taps); prefilter
+                                          // slot: LINEAR or LINEAR_MIPMAP_LINEAR
+  int32_t pad[2];
 };
 
 // pass-level parameters

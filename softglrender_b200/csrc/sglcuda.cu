@@ -65,6 +65,7 @@ struct Ctx {
   // arena
   uint8_t *arena = nullptr;
   size_t arenaCap = 0;
+  void *dummyTexels = nullptr; // backing store of texture table entry 0
   uint32_t *vis = nullptr;     // visibility buffer of the deferred path
   size_t visCap = 0;
   int forceFused = 0;          // SGL_FORCE_FUSED=1: always use the fused tile kernel (A/B runs, tests)
@@ -277,6 +278,19 @@ int sgl_init(int device_ordinal, int rank, int world) {
   CU(cudaMemset(g.dCounters, 0, 8 * sizeof(unsigned long long)));
   CU(cudaEventCreate(&g.evBegin));
   CU(cudaEventCreate(&g.evEnd));
+  {  // texture table entry 0 = 1x1 RGBA8 dummy: what unbound maps read in the straight-line shader paths
+    CU(cudaMalloc(&g.dummyTexels, 256));
+    CU(cudaMemset(g.dummyTexels, 0, 256));
+    SglTexObj &o = g.textures[0].obj;
+    memset(&o, 0, sizeof(o));
+    o.base = (uint8_t *) g.dummyTexels;
+    o.layerStride = 0;
+    o.width = o.height = o.levels = o.layers = o.samples = 1;
+    o.format = SGL_FMT_RGBA8;
+    o.layout = SGL_LAYOUT_LINEAR;
+    int rc0 = uploadTexObj(0);
+    if (rc0) return rc0;
+  }
   {
     const char *ff = getenv("SGL_FORCE_FUSED");
     g.forceFused = (ff && atoi(ff) != 0) ? 1 : 0;
@@ -298,6 +312,7 @@ int sgl_shutdown(void) {
   if (g.dTextures) cudaFree(g.dTextures);
   if (g.arena) cudaFree(g.arena);
   if (g.vis) cudaFree(g.vis);
+  if (g.dummyTexels) cudaFree(g.dummyTexels);
   if (g.dTileOwner) cudaFree(g.dTileOwner);
   if (g.dCounters) cudaFree(g.dCounters);
   for (auto &s : g.staging) {
@@ -676,6 +691,7 @@ int sgl_draw(const SglDraw *draw) {
     float bc = b.border == SGL_BORDER_WHITE ? 1.f : 0.f;
     if (t && t->obj.format == SGL_FMT_FLOAT32) memcpy(&r.samplers[s].border, &bc, 4);
     else r.samplers[s].border = b.border == SGL_BORDER_WHITE ? 0xFFFFFFFFu : 0u;
+    if (t && sglSamplerIsSimple(draw->shader, s, t->obj, b.filter_min, b.wrap)) r.fastSamplers |= 1u << s;
   }
   r.rs = draw->states;
   r.shader = draw->shader;

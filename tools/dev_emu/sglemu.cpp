@@ -93,8 +93,16 @@ int sgl_texture_create(const SglTextureDesc *desc, int *h) {
   *h = (int) textures.size() - 1;
   return 0;
 }
+static uint32_t dummyTexel[64];
 static void fixPtrs() {
   texTable.resize(textures.size());
+  {
+    SglTexObj &o = texTable[0];
+    memset(&o, 0, sizeof(o));
+    o.base = (uint8_t *) dummyTexel;
+    o.width = o.height = o.levels = o.layers = o.samples = 1;
+    o.format = SGL_FMT_RGBA8; o.layout = SGL_LAYOUT_LINEAR;
+  }
   for (size_t i = 1; i < textures.size(); i++) {
     textures[i].obj.base = textures[i].mem.data();
     textures[i].obj.resolve = textures[i].res.empty() ? nullptr : textures[i].res.data();
@@ -157,6 +165,7 @@ int sgl_draw(const SglDraw *draw) {
     float bc = b.border == SGL_BORDER_WHITE ? 1.f : 0.f;
     if (ok && textures[b.texture].obj.format == SGL_FMT_FLOAT32) memcpy(&r.samplers[s].border, &bc, 4);
     else r.samplers[s].border = b.border == SGL_BORDER_WHITE ? 0xFFFFFFFFu : 0u;
+    if (ok) { fixPtrs(); if (sglSamplerIsSimple(draw->shader, s, textures[b.texture].obj, b.filter_min, b.wrap)) r.fastSamplers |= 1u << s; }
   }
   r.rs = draw->states; r.shader = draw->shader; r.defines = draw->defines;
   r.vpX = vpX; r.vpY = vpY; r.vpW = vpW; r.vpH = vpH;
