@@ -8,8 +8,10 @@ A step = one full frame of config 2 (shadow pass 512^2 + main pass 1920x1080 MSA
 skybox), submitted through the Renderer API trace exactly as the Viewer submits it.  `value` = frames/s with all
 inputs resident in HBM; `e2e` adds, per frame, the pinned-host upload of the frame's draw records/uniform snapshots
 and the read-back of the resolved 1920x1080 RGBA8 image into pinned host memory.
-N > 1: one process per GPU (torchrun), frame-parallel (every rank renders K frames -> weak scaling) and every finished
-frame is gathered to rank 0 with NCCL; timing is device-side, max over ranks.
+N > 1: one process per GPU (torchrun).  Default = frame-parallel (every rank renders its own frame per step -> weak
+scaling); `--mgpu tiles` shards ONE frame by screen-tile ownership (strong scaling).  Either way the finished pixels are
+gathered into rank 0's HBM inside the timed region: by direct peer stores from the shading kernel over NVLink (default)
+or by an NCCL gather (`--gather nccl`).  Timing is device-side (CUDA events), max over ranks.
 """
 import argparse
 import json
@@ -91,6 +93,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mgpu", default="frames", choices=["frames", "tiles"],
+                    help="N > 1: frame-parallel (weak scaling, default) or one frame sharded by screen tiles (strong scaling)")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: finished pixels reach rank 0 by direct peer stores from the shading kernel, or by an NCCL gather")
     args = ap.parse_args()
     rank, local_rank, world = _env_rank()
     K, W = args.steps, max(args.warmup, 3)
@@ -102,7 +108,7 @@ def main():
               "resolution": [WIDTH, HEIGHT], "msaa": 4, "draws_per_frame": 6, "passes_per_frame": 2,
               "l2_policy": "inputs larger than L2: ~190 MB touched per frame (96 MB skybox cube + 66 MB MSAA colour/depth + "
                            "20 MB material textures + 8 MB resolve) vs 126 MB L2; no explicit flush",
-              "parallelism": "frame-parallel x%d, finished frames gathered to rank 0 over NCCL" % world if world > 1 else "single GPU"}
+              "parallelism": "single GPU"}
 
     # ---------------------------------------------------------------------------------------------- reference arm
     if args.impl == "reference":
@@ -122,17 +128,23 @@ def main():
         return 0
 
     # ---------------------------------------------------------------------------------------------- RendererCUDA arm
+    import ctypes as C
     import numpy as np
     import torch
     import torch.distributed as dist
-    from softglrender_b200 import capi
+    from softglrender_b200 import capi, multigpu as M
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; RendererCUDA has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    ctl = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        ctl = dist.new_group(backend="gloo")      # control plane (IPC handles); the data plane is NVLink
     capi.init(local_rank, rank, world)
     lib = capi.load()
+    stream = torch.cuda.Stream()                   # the library renders on torch's current stream, so NCCL ops and torch
+    torch.cuda.set_stream(stream)                  # copies are stream-ordered with the kernels (no host waits per frame)
+    capi.check(lib.sgl_set_stream(C.c_void_p(stream.cuda_stream)))
     if rank == 0:
         trace, data = workloads.build_c2(work, WIDTH, HEIGHT)
     if world > 1:
@@ -142,28 +154,61 @@ def main():
     player.setup()
     color_handle = player.texture_handle("color")
     nbytes = WIDTH * HEIGHT * 4
-    host_img = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    host_img = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    host_all = torch.empty(nbytes, dtype=torch.uint8).pin_memory() if (world > 1 and rank == 0 and args.mgpu == "tiles") else None
 
-    # NCCL gather of the finished (resolved) frame to rank 0: a torch view of the library's resolve buffer
-    gather_in = gather_out = None
+    # ---- N > 1: what is sharded and how finished pixels reach rank 0 (softglrender_b200/multigpu.py)
+    tiles = world > 1 and args.mgpu == "tiles"
+    store = gather_in = gather_out = tile_gather = None
+    gather = "none"
     if world > 1:
-        import ctypes as C
-        ptr, sz = C.c_void_p(), C.c_size_t()
-        lib.sgl_texture_device_ptr.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
-        capi.check(lib.sgl_texture_device_ptr(color_handle, 0, 0, 1, C.byref(ptr), C.byref(sz)))
+        if tiles:
+            tile_gather = M.TileGather(WIDTH, HEIGHT, rank, world, "interleave")
+            tile_gather.install(lib)
+        gather = args.gather
+        if gather == "p2p":
+            try:
+                store = M.PeerFrameStore(lib, WIDTH, HEIGHT, rank, world, frames_per_slot=1 if tiles else world, slots=2,
+                                         control_group=ctl)
+            except RuntimeError as e:      # CUDA IPC not permitted on this box (all ranks agree): NCCL moves the same bytes
+                gather = "nccl (p2p unavailable: %s)" % str(e)[:80]
+        if store is None and not tiles:
+            ptr, sz = C.c_void_p(), C.c_size_t()
+            capi.check(lib.sgl_texture_device_ptr(color_handle, 0, 0, 1, C.byref(ptr), C.byref(sz)))
+            gather_in = M.device_view(ptr.value, nbytes)
+            gather_out = [torch.empty(nbytes, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
+    config["parallelism"] = ("single GPU" if world == 1 else
+                             ("sort-first screen-tile ownership x%d (16x16 tiles, 4x4-tile blocks interleaved), geometry replicated" % world
+                              if tiles else "frame-parallel x%d (every rank renders its own frame each step)" % world))
+    config["gather"] = ("n/a" if world == 1 else
+                        ("direct peer stores: the shading kernel writes resolved pixels into rank 0's HBM over NVLink (CUDA IPC), "
+                         "stream-ordered system-scope flags" if store is not None else
+                         "NCCL gather to rank 0 (%s)" % gather))
+    step_no = [0]
 
-        class _Dev:
-            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr.value, False), "version": 3}
-        gather_in = torch.as_tensor(_Dev(), device="cuda")
-        gather_out = [torch.empty(nbytes, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
-
-    def step(readback):
+    def step(e2e):
+        i = step_no[0]
+        step_no[0] += 1
+        if store is not None:
+            store.begin_frame(color_handle, 0 if tiles else rank)
         player.frame(sync=False)
-        if world > 1:
-            capi.check(lib.sgl_wait_idle())      # library stream -> visible to NCCL's stream
+        if store is not None:
+            consume = None
+            if e2e and tiles and rank == 0:     # the assembled frame leaves rank 0's store for the host
+                def consume(ptr):
+                    host_all.copy_(M.device_view(ptr, nbytes), non_blocking=True)
+                    g_d2h[0] += nbytes
+            store.end_frame(consume)
+        elif tile_gather is not None:
+            tile_gather.gather_device(lib, color_handle)
+            if e2e and rank == 0:
+                capi.check(lib.sgl_texture_readback_async(color_handle, 0, 0, 1, host_img[i & 1].data_ptr(), nbytes))
+        elif world > 1:
             dist.gather(gather_in, gather_out, dst=0)
-        if readback:
-            capi.check(lib.sgl_texture_readback(color_handle, 0, 0, 1, host_img.data_ptr(), nbytes))
+        if e2e and not tiles:                   # every rank delivers its own frame to (shared) host memory, pipelined
+            capi.check(lib.sgl_texture_readback_async(color_handle, 0, 0, 1, host_img[i & 1].data_ptr(), nbytes))
+
+    g_d2h = [0]
 
     def sync_all():
         capi.check(lib.sgl_wait_idle())
@@ -188,7 +233,9 @@ def main():
         elapsed_ms = _max_over_ranks(ms.value, world)
     ctr = capi.counters()
 
-    # ---- timed region 2: end to end through the public API with host buffers (upload of per-frame records + read-back)
+    # ---- timed region 2: end to end through the public API with host buffers: per frame the draw records / uniform
+    #      snapshots are uploaded from pinned memory and the finished frame is read back into pinned host memory
+    #      (pipelined: the copy of frame f overlaps the geometry + visibility work of frame f+1)
     capi.check(lib.sgl_reset_counters())
     sync_all()
     t0 = time.perf_counter()
@@ -197,6 +244,11 @@ def main():
     sync_all()
     e2e_s = _max_over_ranks(time.perf_counter() - t0, world)
     ctr2 = capi.counters()
+    h2d = _sum_over_ranks(ctr2["h2d_bytes"], world)
+    d2h = _sum_over_ranks(ctr2["d2h_bytes"] + g_d2h[0], world)
+    timeouts = store.timeouts() if store is not None else 0
+    if timeouts:
+        raise SystemExit("bench.py: %d peer waits timed out on rank %d" % (timeouts, rank))
 
     # ---- per-kernel device times for the roofline block (profiling events on; separate from the timed regions)
     capi.check(lib.sgl_set_profiling(1))
@@ -205,16 +257,19 @@ def main():
     capi.check(lib.sgl_wait_idle())
     ktimes = capi.kernel_times()
     capi.check(lib.sgl_set_profiling(0))
+    sync_all()
 
-    fps = world * K / (elapsed_ms / 1000.0)
-    frags_per_frame = ctr["fragments_shaded"] / float(K)
+    frames_per_step = 1 if tiles or world == 1 else world
+    fps = frames_per_step * K / (elapsed_ms / 1000.0)
+    frags_per_frame = _sum_over_ranks(ctr["fragments_shaded"], world) / float(K * frames_per_step)
+    launches = _sum_over_ranks(ctr["kernel_launches"], world)
     line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "bundled glTF asset + synthetic camera (Config defaults)", "config": config,
+            "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "bundled glTF asset + synthetic camera (Config defaults)", "config": config,
             "gfrag_per_s": fps * frags_per_frame / 1e9, "fragments_per_frame": frags_per_frame,
-            "e2e": {"value": world * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": ctr2["h2d_bytes"] // K,
-                    "d2h_bytes_per_step": ctr2["d2h_bytes"] // K},
-            "gpu_launches": ctr["kernel_launches"], "clocks": clocks.summary()}
+            "e2e": {"value": frames_per_step * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d // K,
+                    "d2h_bytes_per_step": d2h // K},
+            "gpu_launches": launches, "clocks": clocks.summary()}
     if rank == 0:
         line["roofline"] = roofline_block(ktimes, ctr, K, data)
         line["kernel_ms_per_frame"] = {k: v[1] / 20.0 for k, v in sorted(ktimes.items())}
@@ -225,8 +280,19 @@ def main():
                 line["cpu_baseline"] = {"error": str(e)[:200]}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def _sum_over_ranks(v, world):
+    if world == 1:
+        return int(v)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([int(v)], dtype=torch.int64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return int(t.item())
 
 
 def _cuda_ok():

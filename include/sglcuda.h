@@ -144,6 +144,10 @@ int sgl_texture_upload(int handle, int layer, int level, const void *host_data);
 int sgl_texture_gen_mips(int handle);                                   /* SamplerSoft.h:90-110,241-252 */
 /* kind 0: attachment (w*h*samples*4 bytes, [y][x][sample]); kind 1: resolved colour of an MS texture */
 int sgl_texture_readback(int handle, int layer, int level, int kind, void *host_out, size_t bytes);
+/* pipelined form: queued behind all submitted work on a second stream; a later pass that overwrites the image waits for
+ * the copy on the device, the host waits with sgl_readback_wait() (or sgl_wait_idle()).  host_out should be pinned. */
+int sgl_texture_readback_async(int handle, int layer, int level, int kind, void *host_out, size_t bytes);
+int sgl_readback_wait(void);
 int sgl_texture_level_size(int handle, int level, int *w_out, int *h_out);
 int sgl_texture_device_ptr(int handle, int layer, int level, int kind, void **ptr_out, size_t *bytes_out);
 
@@ -159,6 +163,28 @@ int sgl_pass_end(void);
  * the map is supplied explicitly: owner[ty*tiles_x+tx] == rank.  NULL restores "own everything". */
 int sgl_set_tile_owner_map(const uint8_t *owner, int tiles_x, int tiles_y);
 int sgl_tile_size(void);
+int sgl_set_rank(int rank, int world);                     /* re-label the context (sgl_init's rank/world) */
+int sgl_tiles_owned(int owner_rank, int *tiles_out);       /* number of tiles `owner_rank` owns in the current map */
+/* Gather of finished tiles to rank 0, NCCL form: tiles of a linear RGBA8 texture (resolved colour for MS targets) owned by
+ * `owner_rank`, in tile-index order <-> dense device staging buffer [tiles][SGL_TILE][SGL_TILE] RGBA8 that the caller
+ * moves with ncclSend/Recv (torch.distributed); rank 0 unpacks every peer's buffer into its own image.  Queued on the
+ * library's stream. */
+int sgl_tiles_pack(int texture, int owner_rank, void *dst_device, size_t dst_bytes, int *tiles_out);
+int sgl_tiles_unpack(int texture, int owner_rank, const void *src_device, size_t src_bytes);
+/* Gather by direct store over NVLink (no copy step): the final colour of every pass that renders into `texture`
+ * (the MSAA resolve, RendererSoft.cpp:880-912, or the colour of a 1-sample target) is ALSO stored to
+ * device_ptr[y*width+x]; device_ptr may be another GPU's memory mapped with sgl_peer_open.  NULL switches it off. */
+int sgl_texture_set_mirror(int texture, void *device_ptr);
+/* peer memory between the one-process-per-GPU ranks of a box: cudaMalloc + CUDA IPC handle (64 bytes, sent to the peers by
+ * the caller), mapping, and stream-ordered flags: signal = system-scope release store of `value` after all prior work on
+ * the library's stream; wait = bounded spin until `count` flags (64-byte stride) are >= value (wrap-safe compare). */
+int sgl_peer_alloc(size_t bytes, void **ptr_out, uint8_t ipc_handle_out[64]);
+int sgl_peer_free(void *ptr);
+int sgl_peer_open(const uint8_t ipc_handle[64], void **ptr_out);
+int sgl_peer_close(void *ptr);
+int sgl_peer_signal(void *flag_device_ptr, uint32_t value);
+int sgl_peer_wait(const void *flags_device_ptr, int count, uint32_t value, int timeout_ms);
+int sgl_peer_timeouts(uint64_t *count_out);                /* number of waits that gave up (must stay 0) */
 
 /* ---- unit-level entry points used by the known-answer tests (each wraps the device function the pipeline uses) */
 /* barycentric + coverage + depth of RendererSoft::barycentric / rasterizationPixelQuad (RendererSoft.cpp:771-804,1021-1056)

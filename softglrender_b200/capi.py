@@ -52,8 +52,10 @@ C_ABI_SYMBOLS = [
     "sgl_shader_uniform_offset", "sgl_shader_sampler_slot",
     "sgl_shader_define_bit", "sgl_shader_uniform_size", "sgl_shader_varying_floats", "sgl_buffer_create",
     "sgl_buffer_upload", "sgl_buffer_destroy", "sgl_texture_create", "sgl_texture_destroy", "sgl_texture_upload",
-    "sgl_texture_gen_mips", "sgl_texture_readback", "sgl_texture_level_size", "sgl_texture_device_ptr",
+    "sgl_texture_gen_mips", "sgl_texture_readback", "sgl_texture_readback_async", "sgl_readback_wait", "sgl_texture_level_size", "sgl_texture_device_ptr",
     "sgl_pass_begin", "sgl_set_viewport", "sgl_draw", "sgl_pass_end", "sgl_set_tile_owner_map", "sgl_tile_size",
+    "sgl_set_rank", "sgl_tiles_owned", "sgl_tiles_pack", "sgl_tiles_unpack", "sgl_texture_set_mirror", "sgl_peer_alloc",
+    "sgl_peer_free", "sgl_peer_open", "sgl_peer_close", "sgl_peer_signal", "sgl_peer_wait", "sgl_peer_timeouts",
     "sgl_kat_barycentric", "sgl_kat_sample", "sgl_kat_blend", "sgl_kat_depth"]
 
 _lib = None
@@ -82,11 +84,24 @@ def load():
     _lib.sgl_texture_create.argtypes = [C.POINTER(SglTextureDesc), C.POINTER(C.c_int)]
     _lib.sgl_texture_upload.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
     _lib.sgl_texture_readback.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    _lib.sgl_texture_readback_async.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     _lib.sgl_texture_level_size.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib.sgl_pass_begin.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_float]
     _lib.sgl_draw.argtypes = [C.POINTER(SglDraw)]
     _lib.sgl_get_counters.argtypes = [C.POINTER(SglCounters)]
     _lib.sgl_set_tile_owner_map.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    _lib.sgl_tiles_owned.argtypes = [C.c_int, C.POINTER(C.c_int)]
+    _lib.sgl_tiles_pack.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]
+    _lib.sgl_tiles_unpack.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    _lib.sgl_texture_set_mirror.argtypes = [C.c_int, C.c_void_p]
+    _lib.sgl_peer_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]
+    _lib.sgl_peer_free.argtypes = [C.c_void_p]
+    _lib.sgl_peer_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    _lib.sgl_peer_close.argtypes = [C.c_void_p]
+    _lib.sgl_peer_signal.argtypes = [C.c_void_p, C.c_uint32]
+    _lib.sgl_peer_wait.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int]
+    _lib.sgl_peer_timeouts.argtypes = [C.POINTER(C.c_uint64)]
+    _lib.sgl_texture_device_ptr.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     _lib.sgl_shader_uniform_offset.argtypes = [C.c_int, C.c_char_p]
     _lib.sgl_shader_sampler_slot.argtypes = [C.c_int, C.c_char_p]
     _lib.sgl_shader_define_bit.argtypes = [C.c_int, C.c_char_p]

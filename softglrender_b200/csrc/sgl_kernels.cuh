@@ -352,9 +352,11 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS) sglRasterKernel(SglPassParam
             r |= (sum / NS) << (8 * c);     // u8vec4(sum / 4.f) truncation: exact integer division
           }
           reinterpret_cast<uint32_t *>(P.resolveBase)[pix] = r;
+          if (P.mirrorBase) reinterpret_cast<uint32_t *>(P.mirrorBase)[pix] = r;
         }
       } else {
         reinterpret_cast<uint32_t *>(P.colorBase)[pix] = st.color[0];
+        if (P.mirrorBase) reinterpret_cast<uint32_t *>(P.mirrorBase)[pix] = st.color[0];
       }
     }
   }
@@ -394,6 +396,80 @@ __global__ void sglRelayoutKernel(uint32_t *dst, const uint32_t *src, int w, int
   size_t lin = (size_t) y * w + x, til = sglTexelIndex(layout, w, x, y);
   if (toLayout) dst[til] = src[lin];
   else dst[lin] = src[til];
+}
+
+// ---- multi-GPU gather helpers ------------------------------------------------------------------------
+// Tiles owned by `rank` in tile-index order <-> dense [n][SGL_TILE][SGL_TILE] RGBA8 staging buffer (what NCCL moves).
+// grid = tiles, block = SGL_TILE_THREADS; `prefix[t]` = number of tiles owned by `rank` before tile t.
+__global__ void __launch_bounds__(SGL_TILE_THREADS) sglTilePackKernel(uint32_t *image, uint32_t *packed, const uint8_t *owner,
+                                                                     const uint32_t *prefix, int rank, int tilesX, int w, int h,
+                                                                     int unpack) {
+  const int tile = blockIdx.x;
+  if (owner[tile] != rank) return;
+  const int tx = tile % tilesX, ty = tile / tilesX;
+  const int px = tx * SGL_TILE + (threadIdx.x & (SGL_TILE - 1)), py = ty * SGL_TILE + threadIdx.x / SGL_TILE;
+  if (px >= w || py >= h) return;
+  const size_t pi = (size_t) prefix[tile] * SGL_TILE_THREADS + threadIdx.x, ii = (size_t) py * w + px;
+  if (unpack) image[ii] = packed[pi];
+  else packed[pi] = image[ii];
+}
+
+// exclusive count of owned tiles (single CTA; tile maps are a few thousand entries)
+__global__ void __launch_bounds__(1024) sglTileOwnerPrefixKernel(const uint8_t *owner, uint32_t *prefix, int nTiles, int rank) {
+  __shared__ uint32_t sWarp[32];
+  __shared__ uint32_t sCarry;
+  if (threadIdx.x == 0) sCarry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < nTiles; base += 1024) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = (i < nTiles && owner[i] == rank) ? 1u : 0u;
+    const uint32_t ballot = __ballot_sync(0xffffffffu, v);
+    const uint32_t excl = __popc(ballot & ((1u << lane) - 1u));
+    if (lane == 31) sWarp[warp] = __popc(ballot);
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = sWarp[lane], inc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      sWarp[lane] = inc - w;
+    }
+    __syncthreads();
+    const uint32_t e = sCarry + sWarp[warp] + excl;
+    if (i < nTiles) prefix[i] = e;
+    __syncthreads();
+    if (threadIdx.x == 1023) sCarry = e + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) prefix[nTiles] = sCarry;
+}
+
+// Peer-memory flags of the direct-store gather: a release store at system scope after the frame's kernels (stream order),
+// and a bounded spin on `count` consecutive 32-bit flags (stride 64 bytes) until each is >= value.
+__global__ void sglPeerSignalKernel(uint32_t *flag, uint32_t value) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+
+__global__ void sglPeerWaitKernel(const uint32_t *flags, int count, uint32_t value, long long timeoutCycles,
+                                  unsigned long long *counters) {
+  const int i = threadIdx.x;
+  if (i >= count) return;
+  const uint32_t *f = flags + (size_t) i * 16;
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if ((int32_t) (v - value) >= 0) break;
+    if (clock64() - t0 > timeoutCycles) {
+      atomicAdd(counters + 6, 1ull);   // peer wait timed out: surfaced by sgl_peer_check
+      break;
+    }
+    __nanosleep(200);
+  }
 }
 
 __global__ void sglFill32Kernel(uint32_t *dst, uint32_t value, size_t n) {

@@ -298,9 +298,11 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS) sglShadeKernel(SglPassParams
           r |= (sum / NS) << (8 * c);
         }
         reinterpret_cast<uint32_t *>(P.resolveBase)[pix] = r;
+        if (P.mirrorBase) reinterpret_cast<uint32_t *>(P.mirrorBase)[pix] = r;
       }
     } else {
       reinterpret_cast<uint32_t *>(P.colorBase)[pix] = color[0];
+      if (P.mirrorBase) reinterpret_cast<uint32_t *>(P.mirrorBase)[pix] = color[0];
     }
   }
   shaded = __reduce_add_sync(0xffffffffu, shaded);

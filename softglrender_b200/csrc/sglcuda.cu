@@ -36,6 +36,9 @@ struct TextureRec {
   SglTextureDesc desc{};
   SglTexObj obj{};
   size_t bytes = 0;
+  void *mirror = nullptr;   // sgl_texture_set_mirror: second destination of the final colour (may be peer memory)
+  cudaEvent_t rbDone = nullptr;   // completion of the last sgl_texture_readback_async on the copy stream
+  bool rbPending = false;         // a later pass that overwrites the colour image must wait for rbDone on the device
 };
 
 struct Staging {
@@ -50,6 +53,8 @@ struct Ctx {
   int device = 0, rank = 0, world = 1;
   cudaStream_t stream = nullptr;
   bool ownStream = false;
+  cudaStream_t copyStream = nullptr;   // asynchronous read-backs overlap the next frame's geometry / visibility work
+  cudaEvent_t copyReady = nullptr;
   std::vector<BufferRec> buffers{1};
   std::vector<TextureRec> textures{1};
   SglTexObj *dTextures = nullptr;
@@ -74,6 +79,10 @@ struct Ctx {
   // multi-GPU
   uint8_t *dTileOwner = nullptr;
   int ownerTilesX = 0, ownerTilesY = 0;
+  std::vector<uint8_t> hostTileOwner;
+  uint32_t *dOwnerPrefix = nullptr;   // exclusive count of tiles owned by prefixRank (sgl_tiles_pack / unpack)
+  int prefixRank = -1;
+  std::vector<void *> peerAllocs, peerMaps;
   // counters
   unsigned long long *dCounters = nullptr;
   unsigned long long hostLaunches = 0, hostPasses = 0, hostDraws = 0, hostH2D = 0, hostD2H = 0;
@@ -278,6 +287,8 @@ int sgl_init(int device_ordinal, int rank, int world) {
   CU(cudaMemset(g.dCounters, 0, 8 * sizeof(unsigned long long)));
   CU(cudaEventCreate(&g.evBegin));
   CU(cudaEventCreate(&g.evEnd));
+  CU(cudaStreamCreateWithFlags(&g.copyStream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&g.copyReady, cudaEventDisableTiming));
   {  // texture table entry 0 = 1x1 RGBA8 dummy: what unbound maps read in the straight-line shader paths
     CU(cudaMalloc(&g.dummyTexels, 256));
     CU(cudaMemset(g.dummyTexels, 0, 256));
@@ -305,15 +316,22 @@ int sgl_shutdown(void) {
   cudaStreamSynchronize(g.stream);
   for (auto &b : g.buffers)
     if (b.d) cudaFree(b.d);
+  if (g.copyStream) cudaStreamSynchronize(g.copyStream);
   for (auto &t : g.textures) {
     if (t.alive && t.obj.base) cudaFree(t.obj.base);
     if (t.alive && t.obj.resolve) cudaFree(t.obj.resolve);
+    if (t.rbDone) cudaEventDestroy(t.rbDone);
   }
+  if (g.copyStream) cudaStreamDestroy(g.copyStream);
+  if (g.copyReady) cudaEventDestroy(g.copyReady);
   if (g.dTextures) cudaFree(g.dTextures);
   if (g.arena) cudaFree(g.arena);
   if (g.vis) cudaFree(g.vis);
   if (g.dummyTexels) cudaFree(g.dummyTexels);
   if (g.dTileOwner) cudaFree(g.dTileOwner);
+  if (g.dOwnerPrefix) cudaFree(g.dOwnerPrefix);
+  for (void *m : g.peerMaps) cudaIpcCloseMemHandle(m);
+  for (void *a : g.peerAllocs) cudaFree(a);
   if (g.dCounters) cudaFree(g.dCounters);
   for (auto &s : g.staging) {
     if (s.host) cudaFreeHost(s.host);
@@ -343,6 +361,7 @@ int sgl_set_stream(void *cuda_stream) {
 int sgl_wait_idle(void) {
   NEED_CTX();
   CU(cudaStreamSynchronize(g.stream));
+  CU(cudaStreamSynchronize(g.copyStream));
   return SGL_OK;
 }
 
@@ -518,8 +537,10 @@ int sgl_texture_destroy(int handle) {
   TextureRec *t = tex(handle);
   if (!t) return fail(SGL_ERR_INVALID, "bad texture handle %d", handle);
   CU(cudaStreamSynchronize(g.stream));
+  CU(cudaStreamSynchronize(g.copyStream));
   if (t->obj.base) CU(cudaFree(t->obj.base));
   if (t->obj.resolve) CU(cudaFree(t->obj.resolve));
+  if (t->rbDone) cudaEventDestroy(t->rbDone);
   *t = TextureRec();
   return SGL_OK;
 }
@@ -617,6 +638,42 @@ int sgl_texture_readback(int handle, int layer, int level, int kind, void *host_
   CU(cudaStreamSynchronize(g.stream));
   CU(cudaMemcpy(host_out, tmp, need, cudaMemcpyDeviceToHost));
   CU(cudaFree(tmp));
+  return SGL_OK;
+}
+
+// Pipelined read-back: the copy is queued on a second stream behind everything submitted so far and runs while the
+// next frame's vertex / setup / binning / visibility kernels execute; a later pass that overwrites the image waits for
+// the copy on the device (sgl_pass_end), so the caller never has to fence.  The host buffer should be pinned.
+int sgl_texture_readback_async(int handle, int layer, int level, int kind, void *host_out, size_t bytes) {
+  NEED_CTX();
+  TextureRec *t = tex(handle);
+  if (!t || layer < 0 || layer >= t->obj.layers || level < 0 || level >= t->obj.levels) return fail(SGL_ERR_INVALID, "bad texture/layer/level");
+  if (t->obj.format != SGL_FMT_RGBA8 || t->obj.layout != SGL_LAYOUT_LINEAR) return fail(SGL_ERR_INVALID, "async read-back needs a linear RGBA8 texture");
+  int w = sglLevelDim(t->obj.width, level), h = sglLevelDim(t->obj.height, level);
+  const uint8_t *src;
+  size_t need;
+  if (kind == 1) {
+    if (!t->obj.resolve) return fail(SGL_ERR_INVALID, "texture has no resolved colour buffer");
+    src = t->obj.resolve;
+    need = (size_t) w * h * 4;
+  } else {
+    src = levelPtr(*t, layer, level);
+    need = (size_t) w * h * 4 * t->obj.samples;
+  }
+  if (bytes < need) return fail(SGL_ERR_INVALID, "readback buffer too small");
+  if (!t->rbDone) CU(cudaEventCreateWithFlags(&t->rbDone, cudaEventDisableTiming));
+  CU(cudaEventRecord(g.copyReady, g.stream));
+  CU(cudaStreamWaitEvent(g.copyStream, g.copyReady, 0));
+  CU(cudaMemcpyAsync(host_out, src, need, cudaMemcpyDeviceToHost, g.copyStream));
+  CU(cudaEventRecord(t->rbDone, g.copyStream));
+  t->rbPending = true;
+  g.hostD2H += need;
+  return SGL_OK;
+}
+
+int sgl_readback_wait(void) {
+  NEED_CTX();
+  CU(cudaStreamSynchronize(g.copyStream));
   return SGL_OK;
 }
 
@@ -820,6 +877,7 @@ int sgl_pass_end(void) {
   P.colorBase = ct ? levelPtr(*ct, g.colorLayer, g.colorLevel) : nullptr;
   P.depthBase = dt ? (float *) levelPtr(*dt, 0, 0) : nullptr;
   P.resolveBase = (ct && samples > 1) ? ct->obj.resolve : nullptr;
+  P.mirrorBase = (ct && g.colorLayer == 0 && g.colorLevel == 0) ? (uint8_t *) ct->mirror : nullptr;
   P.fbW = fbW; P.fbH = fbH; P.samples = samples;
   P.clearColorFlag = g.clearColorFlag;
   P.clearDepthFlag = g.clearDepthFlag;
@@ -941,6 +999,10 @@ int sgl_pass_end(void) {
     g.hostLaunches++;
     if (e != 0) return fail(SGL_ERR_CUDA, "visibility kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
     if (ct) {
+      if (ct->rbPending) {   // an asynchronous read-back of this image is still in flight: overwrite only after it
+        CU(cudaStreamWaitEvent(g.stream, ct->rbDone, 0));
+        ct->rbPending = false;
+      }
       profBegin(samples == 4 ? "sglShadeKernel<4>" : "sglShadeKernel<1>");
       e = samples == 4 ? sglLaunchShade4(&P, nTiles, (void *) g.stream) : sglLaunchShade1(&P, nTiles, (void *) g.stream);
       profEnd();
@@ -948,6 +1010,10 @@ int sgl_pass_end(void) {
       if (e != 0) return fail(SGL_ERR_CUDA, "shading kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
     }
   } else {
+    if (ct && ct->rbPending) {
+      CU(cudaStreamWaitEvent(g.stream, ct->rbDone, 0));
+      ct->rbPending = false;
+    }
     profBegin(samples == 4 ? "sglRasterKernel<4>" : "sglRasterKernel<1>");
     int e = samples == 4 ? sglLaunchRaster4(&P, nTiles, (void *) g.stream) : sglLaunchRaster1(&P, nTiles, (void *) g.stream);
     profEnd();
@@ -967,14 +1033,171 @@ int sgl_set_tile_owner_map(const uint8_t *owner, int tiles_x, int tiles_y) {
   NEED_CTX();
   CU(cudaStreamSynchronize(g.stream));
   if (g.dTileOwner) CU(cudaFree(g.dTileOwner));
+  if (g.dOwnerPrefix) CU(cudaFree(g.dOwnerPrefix));
   g.dTileOwner = nullptr;
+  g.dOwnerPrefix = nullptr;
+  g.prefixRank = -1;
   g.ownerTilesX = g.ownerTilesY = 0;
+  g.hostTileOwner.clear();
   if (!owner) return SGL_OK;
   if (tiles_x <= 0 || tiles_y <= 0) return fail(SGL_ERR_INVALID, "bad tile map size");
-  CU(cudaMalloc(&g.dTileOwner, (size_t) tiles_x * tiles_y));
-  CU(cudaMemcpy(g.dTileOwner, owner, (size_t) tiles_x * tiles_y, cudaMemcpyHostToDevice));
+  const size_t n = (size_t) tiles_x * tiles_y;
+  CU(cudaMalloc(&g.dTileOwner, n));
+  CU(cudaMemcpy(g.dTileOwner, owner, n, cudaMemcpyHostToDevice));
+  CU(cudaMalloc(&g.dOwnerPrefix, (n + 1) * sizeof(uint32_t)));
+  g.hostTileOwner.assign(owner, owner + n);
   g.ownerTilesX = tiles_x;
   g.ownerTilesY = tiles_y;
+  return SGL_OK;
+}
+
+int sgl_set_rank(int rank, int world) {
+  NEED_CTX();
+  if (world < 1 || rank < 0 || rank >= world) return fail(SGL_ERR_INVALID, "rank %d of %d", rank, world);
+  g.rank = rank;
+  g.world = world;
+  return SGL_OK;
+}
+
+int sgl_texture_set_mirror(int handle, void *device_ptr) {
+  NEED_CTX();
+  TextureRec *t = tex(handle);
+  if (!t) return fail(SGL_ERR_INVALID, "bad texture handle %d", handle);
+  if (t->obj.format != SGL_FMT_RGBA8 || t->obj.layout != SGL_LAYOUT_LINEAR || t->obj.layers != 1)
+    return fail(SGL_ERR_INVALID, "mirror target needs a linear 2D RGBA8 texture");
+  t->mirror = device_ptr;
+  return SGL_OK;
+}
+
+namespace {
+// image (layer 0 / level 0, resolved colour for MS textures) of a tile-gather operand, and the owner-prefix table
+int tileGatherOperand(int handle, int owner_rank, uint32_t **image, int *w, int *h, int *owned) {
+  TextureRec *t = tex(handle);
+  if (!t) return fail(SGL_ERR_INVALID, "bad texture handle %d", handle);
+  if (t->obj.format != SGL_FMT_RGBA8 || t->obj.layout != SGL_LAYOUT_LINEAR) return fail(SGL_ERR_INVALID, "tile gather needs a linear RGBA8 texture");
+  *w = t->obj.width;
+  *h = t->obj.height;
+  *image = (uint32_t *) (t->obj.samples > 1 ? t->obj.resolve : t->obj.base);
+  if (!*image) return fail(SGL_ERR_INVALID, "texture has no single-sample colour image");
+  const int tilesX = (*w + SGL_TILE - 1) / SGL_TILE, tilesY = (*h + SGL_TILE - 1) / SGL_TILE;
+  if (!g.dTileOwner || g.ownerTilesX != tilesX || g.ownerTilesY != tilesY)
+    return fail(SGL_ERR_STATE, "no tile owner map for a %dx%d-tile target", tilesX, tilesY);
+  const int n = tilesX * tilesY;
+  if (g.prefixRank != owner_rank) {
+    int rc = launch("sglTileOwnerPrefixKernel", sglTileOwnerPrefixKernel, dim3(1), dim3(1024), (const uint8_t *) g.dTileOwner, g.dOwnerPrefix, n, owner_rank);
+    if (rc) return rc;
+    g.prefixRank = owner_rank;
+  }
+  int c = 0;
+  for (int i = 0; i < n; i++) c += g.hostTileOwner[i] == owner_rank;
+  *owned = c;
+  return SGL_OK;
+}
+}  // namespace
+
+int sgl_tiles_owned(int owner_rank, int *tiles_out) {
+  NEED_CTX();
+  if (g.hostTileOwner.empty()) return fail(SGL_ERR_STATE, "no tile owner map");
+  int c = 0;
+  for (uint8_t o : g.hostTileOwner) c += o == owner_rank;
+  *tiles_out = c;
+  return SGL_OK;
+}
+
+int sgl_tiles_pack(int handle, int owner_rank, void *dst_device, size_t dst_bytes, int *tiles_out) {
+  NEED_CTX();
+  uint32_t *image;
+  int w, h, owned;
+  int rc = tileGatherOperand(handle, owner_rank, &image, &w, &h, &owned);
+  if (rc) return rc;
+  if (tiles_out) *tiles_out = owned;
+  if ((size_t) owned * SGL_TILE_THREADS * 4 > dst_bytes) return fail(SGL_ERR_INVALID, "tile staging buffer too small (%d tiles)", owned);
+  return launch("sglTilePackKernel", sglTilePackKernel, dim3(g.ownerTilesX * g.ownerTilesY), dim3(SGL_TILE_THREADS), image, (uint32_t *) dst_device,
+                (const uint8_t *) g.dTileOwner, (const uint32_t *) g.dOwnerPrefix, owner_rank, g.ownerTilesX, w, h, 0);
+}
+
+int sgl_tiles_unpack(int handle, int owner_rank, const void *src_device, size_t src_bytes) {
+  NEED_CTX();
+  uint32_t *image;
+  int w, h, owned;
+  int rc = tileGatherOperand(handle, owner_rank, &image, &w, &h, &owned);
+  if (rc) return rc;
+  if ((size_t) owned * SGL_TILE_THREADS * 4 > src_bytes) return fail(SGL_ERR_INVALID, "tile staging buffer too small (%d tiles)", owned);
+  return launch("sglTilePackKernel", sglTilePackKernel, dim3(g.ownerTilesX * g.ownerTilesY), dim3(SGL_TILE_THREADS), image, (uint32_t *) src_device,
+                (const uint8_t *) g.dTileOwner, (const uint32_t *) g.dOwnerPrefix, owner_rank, g.ownerTilesX, w, h, 1);
+}
+
+// ---- peer memory (one process per GPU; buffers are shared through CUDA IPC handles) --------------------------------
+int sgl_peer_alloc(size_t bytes, void **ptr_out, uint8_t ipc_handle_out[64]) {
+  NEED_CTX();
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, std::max<size_t>(bytes, 256));
+  if (e != cudaSuccess) return fail(SGL_ERR_OOM, "peer buffer of %zu bytes: %s", bytes, cudaGetErrorString(e));
+  CU(cudaMemset(p, 0, std::max<size_t>(bytes, 256)));
+  cudaIpcMemHandle_t hd;
+  e = cudaIpcGetMemHandle(&hd, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(SGL_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  }
+  memcpy(ipc_handle_out, &hd, 64);
+  g.peerAllocs.push_back(p);
+  *ptr_out = p;
+  return SGL_OK;
+}
+
+int sgl_peer_free(void *ptr) {
+  NEED_CTX();
+  auto it = std::find(g.peerAllocs.begin(), g.peerAllocs.end(), ptr);
+  if (it == g.peerAllocs.end()) return fail(SGL_ERR_INVALID, "not a peer allocation");
+  CU(cudaStreamSynchronize(g.stream));
+  CU(cudaFree(ptr));
+  g.peerAllocs.erase(it);
+  return SGL_OK;
+}
+
+int sgl_peer_open(const uint8_t ipc_handle[64], void **ptr_out) {
+  NEED_CTX();
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, ipc_handle, 64);
+  void *p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return fail(SGL_ERR_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+  g.peerMaps.push_back(p);
+  *ptr_out = p;
+  return SGL_OK;
+}
+
+int sgl_peer_close(void *ptr) {
+  NEED_CTX();
+  auto it = std::find(g.peerMaps.begin(), g.peerMaps.end(), ptr);
+  if (it == g.peerMaps.end()) return fail(SGL_ERR_INVALID, "not a peer mapping");
+  CU(cudaStreamSynchronize(g.stream));
+  CU(cudaIpcCloseMemHandle(ptr));
+  g.peerMaps.erase(it);
+  return SGL_OK;
+}
+
+int sgl_peer_signal(void *flag_device_ptr, uint32_t value) {
+  NEED_CTX();
+  return launch("sglPeerSignalKernel", sglPeerSignalKernel, dim3(1), dim3(1), (uint32_t *) flag_device_ptr, value);
+}
+
+int sgl_peer_wait(const void *flags_device_ptr, int count, uint32_t value, int timeout_ms) {
+  NEED_CTX();
+  if (count < 1 || count > 1024) return fail(SGL_ERR_INVALID, "peer wait on %d flags", count);
+  long long cycles = (long long) std::max(timeout_ms, 1) * 2000000LL;   // ~2 GHz SM clock
+  return launch("sglPeerWaitKernel", sglPeerWaitKernel, dim3(1), dim3((unsigned) ((count + 31) / 32 * 32)), (const uint32_t *) flags_device_ptr, count, value,
+                cycles, g.dCounters);
+}
+
+int sgl_peer_timeouts(uint64_t *count_out) {
+  NEED_CTX();
+  unsigned long long c = 0;
+  CU(cudaStreamSynchronize(g.stream));
+  CU(cudaMemcpy(&c, g.dCounters + 6, sizeof(c), cudaMemcpyDeviceToHost));
+  *count_out = c;
   return SGL_OK;
 }
 

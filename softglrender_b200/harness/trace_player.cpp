@@ -113,7 +113,8 @@ bool TracePlayer::readbackTagged(const std::string &tag, PlayerBackend::Blob &ou
     if (r.str() != tag) continue;
     Texture *t = texture(tex);
     if (!t) return false;
-    return PlayerBackend::readback(*t, layer, level, t->multiSample ? 1 : 0, out);
+    // resolved colour for multisample colour targets; the attachment itself (per-sample data) otherwise
+    return PlayerBackend::readback(*t, layer, level, (t->multiSample && t->format == TextureFormat_RGBA8) ? 1 : 0, out);
   }
   return false;
 }
