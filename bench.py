@@ -226,8 +226,10 @@ def main():
         ms = C_float()
         sync_all()
         capi.check(lib.sgl_timer_begin())
+        h0 = time.perf_counter()
         for _ in range(K):
             step(False)
+        host_submit_ms = (time.perf_counter() - h0) * 1e3 / K      # CPU time to record + submit one frame (asynchronous)
         capi.check(lib.sgl_timer_end(ms))
         sync_all()
         elapsed_ms = _max_over_ranks(ms.value, world)
@@ -269,7 +271,7 @@ def main():
             "gfrag_per_s": fps * frags_per_frame / 1e9, "fragments_per_frame": frags_per_frame,
             "e2e": {"value": frames_per_step * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d // K,
                     "d2h_bytes_per_step": d2h // K},
-            "gpu_launches": launches, "clocks": clocks.summary()}
+            "gpu_launches": launches, "clocks": clocks.summary(), "host_submit_ms_per_step": host_submit_ms}
     if rank == 0:
         line["roofline"] = roofline_block(ktimes, ctr, K, data)
         line["kernel_ms_per_frame"] = {k: v[1] / 20.0 for k, v in sorted(ktimes.items())}

@@ -137,9 +137,12 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS, 4) sglVisKernel(SglPassParam
   const int tile = blockIdx.x;
   if (P.tileOwner && P.tileOwner[tile] != P.rank) return;
   const int tx = tile % P.tilesX, ty = tile / P.tilesX;
-  const int tid = threadIdx.x;
-  const int px = tx * SGL_TILE + (tid & (SGL_TILE - 1));
-  const int py = ty * SGL_TILE + (tid / SGL_TILE);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // a warp owns an 8x4 pixel block of the tile (same mapping as the shading kernel): small triangles then concern one
+  // or two warps of the CTA instead of most 16x2 strips
+  const int wbx = tx * SGL_TILE + (warp & 1) * 8, wby = ty * SGL_TILE + (warp >> 1) * 4;
+  const int px = wbx + (lane & 7);
+  const int py = wby + (lane >> 3);
   const bool inFb = px < P.fbW && py < P.fbH;
   const bool hasColor = P.colorBase != nullptr, hasDepth = P.depthBase != nullptr;
   const size_t pix = (size_t) py * P.fbW + px;
@@ -210,8 +213,35 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS, 4) sglVisKernel(SglPassParam
       __syncthreads();
       if (tid < nb && (sPrims[tid].p.flags & SGL_PF_KIND_MASK) == SGL_PK_TRIANGLE) sPrims[tid].e = sglTriEdge(sPrims[tid].p);
       __syncthreads();
+      // warp-level cull: each lane tests two records of the batch against the warp's 8x4 block (bbox, then the same
+      // conservative outside test the pixels use, over the block's sample positions); the warp then visits only the
+      // surviving records, in order
+      uint32_t rel[2];
+#pragma unroll
+      for (int hh = 0; hh < 2; hh++) {
+        const int idx = hh * 32 + lane;
+        bool r = false;
+        if (idx < nb) {
+          const SglVisPrim &vp = sPrims[idx];
+          r = vp.p.bx0 <= wbx + 7 && vp.p.bx1 >= wbx && vp.p.by0 <= wby + 3 && vp.p.by1 >= wby;
+          if (r) {
+            const uint32_t kind = vp.p.flags & SGL_PF_KIND_MASK;
+            if (kind == SGL_PK_TRIANGLE) r = !sglTriSurelyOutside(vp.e, (float) wbx + 4.f, (float) wby + 2.f, 3.875f, 1.875f);
+            else if (kind == SGL_PK_LINE) r = sglLineNearRect(vp.p, wbx, wby, wbx + 7, wby + 3);
+          }
+        }
+        rel[hh] = __ballot_sync(0xffffffffu, r);
+      }
       if (inFb) {
-        for (int k = 0; k < nb; k++) sglVisPixelPrim<NS>(P, sPrims[k], sSlots[b0 + k], px, py, depth, owner, hasColor, hasDepth);
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          uint32_t m = rel[hh];
+          while (m) {
+            const int k = hh * 32 + __ffs(m) - 1;
+            m &= m - 1;
+            sglVisPixelPrim<NS>(P, sPrims[k], sSlots[b0 + k], px, py, depth, owner, hasColor, hasDepth);
+          }
+        }
       }
     }
     __syncthreads();

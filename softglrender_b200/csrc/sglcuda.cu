@@ -67,9 +67,18 @@ struct Ctx {
   float clearDepth = 1.f;
   float vpX = 0, vpY = 0, vpW = 0, vpH = 0;
   std::vector<SglDrawRec> draws;
-  // arena
-  uint8_t *arena = nullptr;
-  size_t arenaCap = 0;
+  // pass arenas: a ring, so that the geometry stages of a pass (vertex, setup, scan, bin fill -- they touch only the
+  // arena) run on their own stream while the pixel stages (visibility, shading) of the previous passes are still busy
+  struct Arena {
+    uint8_t *mem = nullptr;
+    size_t cap = 0;
+    cudaEvent_t geomDone = nullptr, pixelDone = nullptr;
+    bool used = false;
+  };
+  Arena arenas[3];
+  int arenaNext = 0;
+  cudaStream_t geomStream = nullptr;
+  int noOverlap = 0;           // SGL_NO_OVERLAP=1: geometry and pixel stages on one stream (A/B runs)
   void *dummyTexels = nullptr; // backing store of texture table entry 0
   uint32_t *vis = nullptr;     // visibility buffer of the deferred path
   size_t visCap = 0;
@@ -149,18 +158,27 @@ uint8_t *levelPtr(const TextureRec &t, int layer, int level) {
   return t.obj.base + (size_t) layer * t.obj.layerStride + t.obj.levelOffset[level];
 }
 
-int ensureArena(size_t bytes) {
-  if (bytes <= g.arenaCap) return SGL_OK;
+int syncAll() {
   CU(cudaStreamSynchronize(g.stream));
-  if (g.arena) CU(cudaFree(g.arena));
-  g.arena = nullptr;
-  size_t ncap = alignUp(bytes + bytes / 4, 1 << 20);
-  cudaError_t e = cudaMalloc(&g.arena, ncap);
-  if (e != cudaSuccess) {
-    g.arenaCap = 0;
-    return fail(SGL_ERR_OOM, "pass arena of %zu bytes: %s", ncap, cudaGetErrorString(e));
+  if (g.geomStream) CU(cudaStreamSynchronize(g.geomStream));
+  return SGL_OK;
+}
+
+int ensureArena(Ctx::Arena &a, size_t bytes) {
+  if (!a.geomDone) {
+    CU(cudaEventCreateWithFlags(&a.geomDone, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&a.pixelDone, cudaEventDisableTiming));
   }
-  g.arenaCap = ncap;
+  if (bytes <= a.cap) return SGL_OK;
+  int rc = syncAll();
+  if (rc) return rc;
+  if (a.mem) CU(cudaFree(a.mem));
+  a.mem = nullptr;
+  a.cap = 0;
+  size_t ncap = alignUp(bytes + bytes / 4, 1 << 20);
+  cudaError_t e = cudaMalloc(&a.mem, ncap);
+  if (e != cudaSuccess) return fail(SGL_ERR_OOM, "pass arena of %zu bytes: %s", ncap, cudaGetErrorString(e));
+  a.cap = ncap;
   return SGL_OK;
 }
 
@@ -232,21 +250,23 @@ cudaEvent_t profEvent() {
   }
   return e;
 }
+cudaStream_t gCur = nullptr;   // stream of the stage being issued (null = the context's main stream)
+cudaStream_t curStream() { return gCur ? gCur : g.stream; }
 void profBegin(const char *name) {
   if (!gProfiling) return;
   ProfEvent p = {name, profEvent(), profEvent()};
-  cudaEventRecord(p.a, g.stream);
+  cudaEventRecord(p.a, curStream());
   gProf.push_back(p);
 }
 void profEnd() {
   if (!gProfiling) return;
-  cudaEventRecord(gProf.back().b, g.stream);
+  cudaEventRecord(gProf.back().b, curStream());
 }
 
 template<typename... Args>
 int launch(const char *name, void (*kernel)(Args...), dim3 grid, dim3 block, Args... args) {
   profBegin(name);
-  kernel<<<grid, block, 0, g.stream>>>(args...);
+  kernel<<<grid, block, 0, curStream()>>>(args...);
   profEnd();
   g.hostLaunches++;
   cudaError_t e = cudaGetLastError();
@@ -287,6 +307,7 @@ int sgl_init(int device_ordinal, int rank, int world) {
   CU(cudaMemset(g.dCounters, 0, 8 * sizeof(unsigned long long)));
   CU(cudaEventCreate(&g.evBegin));
   CU(cudaEventCreate(&g.evEnd));
+  CU(cudaStreamCreateWithFlags(&g.geomStream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&g.copyStream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&g.copyReady, cudaEventDisableTiming));
   {  // texture table entry 0 = 1x1 RGBA8 dummy: what unbound maps read in the straight-line shader paths
@@ -305,6 +326,8 @@ int sgl_init(int device_ordinal, int rank, int world) {
   {
     const char *ff = getenv("SGL_FORCE_FUSED");
     g.forceFused = (ff && atoi(ff) != 0) ? 1 : 0;
+    const char *no = getenv("SGL_NO_OVERLAP");
+    g.noOverlap = (no && atoi(no) != 0) ? 1 : 0;
   }
   g.ready = true;
   g.err.clear();
@@ -314,6 +337,7 @@ int sgl_init(int device_ordinal, int rank, int world) {
 int sgl_shutdown(void) {
   if (!g.ready) return SGL_OK;
   cudaStreamSynchronize(g.stream);
+  if (g.geomStream) cudaStreamSynchronize(g.geomStream);
   for (auto &b : g.buffers)
     if (b.d) cudaFree(b.d);
   if (g.copyStream) cudaStreamSynchronize(g.copyStream);
@@ -325,7 +349,12 @@ int sgl_shutdown(void) {
   if (g.copyStream) cudaStreamDestroy(g.copyStream);
   if (g.copyReady) cudaEventDestroy(g.copyReady);
   if (g.dTextures) cudaFree(g.dTextures);
-  if (g.arena) cudaFree(g.arena);
+  for (auto &a : g.arenas) {
+    if (a.mem) cudaFree(a.mem);
+    if (a.geomDone) cudaEventDestroy(a.geomDone);
+    if (a.pixelDone) cudaEventDestroy(a.pixelDone);
+  }
+  if (g.geomStream) cudaStreamDestroy(g.geomStream);
   if (g.vis) cudaFree(g.vis);
   if (g.dummyTexels) cudaFree(g.dummyTexels);
   if (g.dTileOwner) cudaFree(g.dTileOwner);
@@ -346,7 +375,7 @@ int sgl_shutdown(void) {
 
 int sgl_set_stream(void *cuda_stream) {
   NEED_CTX();
-  CU(cudaStreamSynchronize(g.stream));
+  { int rc = syncAll(); if (rc) return rc; }
   if (g.ownStream && g.stream) cudaStreamDestroy(g.stream);
   if (cuda_stream) {
     g.stream = (cudaStream_t) cuda_stream;
@@ -360,7 +389,7 @@ int sgl_set_stream(void *cuda_stream) {
 
 int sgl_wait_idle(void) {
   NEED_CTX();
-  CU(cudaStreamSynchronize(g.stream));
+  { int rc = syncAll(); if (rc) return rc; }
   CU(cudaStreamSynchronize(g.copyStream));
   return SGL_OK;
 }
@@ -368,7 +397,7 @@ int sgl_wait_idle(void) {
 int sgl_get_counters(SglCounters *out) {
   NEED_CTX();
   unsigned long long c[8];
-  CU(cudaStreamSynchronize(g.stream));
+  { int rc = syncAll(); if (rc) return rc; }
   CU(cudaMemcpy(c, g.dCounters, sizeof(c), cudaMemcpyDeviceToHost));
   out->passes = g.hostPasses;
   out->draws = g.hostDraws;
@@ -385,7 +414,7 @@ int sgl_get_counters(SglCounters *out) {
 
 int sgl_reset_counters(void) {
   NEED_CTX();
-  CU(cudaStreamSynchronize(g.stream));
+  { int rc = syncAll(); if (rc) return rc; }
   CU(cudaMemset(g.dCounters, 0, 8 * sizeof(unsigned long long)));
   g.hostLaunches = g.hostPasses = g.hostDraws = g.hostH2D = g.hostD2H = 0;
   return SGL_OK;
@@ -414,6 +443,7 @@ int sgl_set_profiling(int on) {
 int sgl_get_kernel_times(SglKernelTime *out, int capacity) {
   if (!g.ready) return 0;
   cudaStreamSynchronize(g.stream);
+  if (g.geomStream) cudaStreamSynchronize(g.geomStream);
   int n = 0;
   for (auto &p : gProf) {
     float ms = 0.f;
@@ -480,6 +510,7 @@ int sgl_buffer_upload(int handle, size_t offset, size_t bytes, const void *host_
   BufferRec &b = g.buffers[handle];
   if (offset > b.bytes) return SGL_OK;
   bytes = std::min(bytes, b.bytes - offset);   // updateVertexData clamps to the buffer size (VertexSoft.h:29-31)
+  { int rc = syncAll(); if (rc) return rc; }   // passes already submitted read the old contents
   CU(cudaMemcpyAsync((uint8_t *) b.d + offset, host_data, bytes, cudaMemcpyHostToDevice, g.stream));
   CU(cudaStreamSynchronize(g.stream));
   return SGL_OK;
@@ -488,7 +519,7 @@ int sgl_buffer_upload(int handle, size_t offset, size_t bytes, const void *host_
 int sgl_buffer_destroy(int handle) {
   NEED_CTX();
   if (handle <= 0 || handle >= (int) g.buffers.size()) return fail(SGL_ERR_INVALID, "bad buffer handle %d", handle);
-  CU(cudaStreamSynchronize(g.stream));
+  { int rc = syncAll(); if (rc) return rc; }
   if (g.buffers[handle].d) CU(cudaFree(g.buffers[handle].d));
   g.buffers[handle] = BufferRec();
   return SGL_OK;
@@ -846,9 +877,33 @@ int sgl_pass_end(void) {
   // depth-only path: the region holds 64-byte work items instead (>= 2 per primitive slot + one per 512 framebuffer pixels)
   if (depthOnly) binCapacity = ((size_t) primSlots * 2 + (size_t) fbW * fbH / 512 + 65536) * (sizeof(SglPrim) / sizeof(uint32_t));
   size_t oBins = take(sizeof(uint32_t) * binCapacity);
-  int rc = ensureArena(off);
+  Ctx::Arena &arena = g.arenas[g.arenaNext];
+  g.arenaNext = (g.arenaNext + 1) % 3;
+  int rc = ensureArena(arena, off);
   if (rc) return rc;
-  uint8_t *A = g.arena;
+  uint8_t *A = arena.mem;
+  // geometry stages go to their own stream unless overlap is off or per-kernel profiling wants clean timings;
+  // the arena slot is recycled only after the pixel stages of the pass that used it last have finished
+  const bool overlap = !g.noOverlap && !gProfiling;
+  struct StageGuard { ~StageGuard() { gCur = nullptr; } } stageGuard;
+  gCur = overlap ? g.geomStream : g.stream;
+  if (arena.used && overlap) CU(cudaStreamWaitEvent(g.geomStream, arena.pixelDone, 0));
+  auto toPixelStage = [&]() -> int {   // everything issued so far on the geometry stream precedes what follows
+    if (gCur != g.stream) {
+      CU(cudaEventRecord(arena.geomDone, g.geomStream));
+      CU(cudaStreamWaitEvent(g.stream, arena.geomDone, 0));
+    }
+    gCur = g.stream;
+    return SGL_OK;
+  };
+  auto passDone = [&]() -> int {
+    CU(cudaEventRecord(arena.pixelDone, g.stream));
+    arena.used = true;
+    g.hostPasses++;
+    g.hostDraws += nDraws;
+    g.draws.clear();
+    return SGL_OK;
+  };
 
   for (int i = 0; i < nDraws; i++) {
     SglDrawRec &r = g.draws[i];
@@ -860,15 +915,15 @@ int sgl_pass_end(void) {
     r.vertexCounter = (int32_t *) (A + oDrawCounters) + 2 * i;
     r.appendCounter = (int32_t *) (A + oDrawCounters) + 2 * i + 1;
   }
-  CU(cudaMemsetAsync(A + oZero, 0, zeroBytes, g.stream));
+  CU(cudaMemsetAsync(A + oZero, 0, zeroBytes, gCur));
   if (nDraws) {
     Staging *st = nullptr;
     rc = stagingAcquire(sizeof(SglDrawRec) * nDraws, &st);
     if (rc) return rc;
     memcpy(st->host, g.draws.data(), sizeof(SglDrawRec) * nDraws);
-    CU(cudaMemcpyAsync(A + oDraws, st->host, sizeof(SglDrawRec) * nDraws, cudaMemcpyHostToDevice, g.stream));
+    CU(cudaMemcpyAsync(A + oDraws, st->host, sizeof(SglDrawRec) * nDraws, cudaMemcpyHostToDevice, gCur));
     g.hostH2D += sizeof(SglDrawRec) * nDraws;
-    CU(cudaEventRecord(st->done, g.stream));
+    CU(cudaEventRecord(st->done, gCur));
     st->pending = true;
   }
 
@@ -912,6 +967,8 @@ int sgl_pass_end(void) {
       rc = launch("sglVertexKernel", sglVertexKernel, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws);
       if (rc) return rc;
     }
+    rc = toPixelStage();   // the atomic rasteriser writes the depth attachment
+    if (rc) return rc;
     if (g.clearDepthFlag) {
       uint32_t bits;
       memcpy(&bits, &g.clearDepth, 4);
@@ -943,10 +1000,7 @@ int sgl_pass_end(void) {
       g.hostLaunches += 3;
       if (e != 0) return fail(SGL_ERR_CUDA, "depth-only kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
     }
-    g.hostPasses++;
-    g.hostDraws += nDraws;
-    g.draws.clear();
-    return SGL_OK;
+    return passDone();
   }
 
   if (nDraws) {
@@ -970,6 +1024,8 @@ int sgl_pass_end(void) {
     rc = launch("sglBinFillKernel", sglBinFillKernel, dim3((maxSlots + 255) / 256, nDraws), dim3(256), P);
     if (rc) return rc;
   }
+  rc = toPixelStage();
+  if (rc) return rc;
   // Deferred (visibility + shading) path for passes made of opaque draws whose point/line programs have no varyings;
   // everything else (blending, wireframe with a lit program) takes the fused tile kernel.
   bool deferred = !g.forceFused;
@@ -1020,10 +1076,7 @@ int sgl_pass_end(void) {
     g.hostLaunches++;
     if (e != 0) return fail(SGL_ERR_CUDA, "raster kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
   }
-  g.hostPasses++;
-  g.hostDraws += nDraws;
-  g.draws.clear();
-  return SGL_OK;
+  return passDone();
 }
 
 // ---- multi-GPU --------------------------------------------------------------------------------------------------
@@ -1031,7 +1084,7 @@ int sgl_tile_size(void) { return SGL_TILE; }
 
 int sgl_set_tile_owner_map(const uint8_t *owner, int tiles_x, int tiles_y) {
   NEED_CTX();
-  CU(cudaStreamSynchronize(g.stream));
+  { int rc = syncAll(); if (rc) return rc; }
   if (g.dTileOwner) CU(cudaFree(g.dTileOwner));
   if (g.dOwnerPrefix) CU(cudaFree(g.dOwnerPrefix));
   g.dTileOwner = nullptr;

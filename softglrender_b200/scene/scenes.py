@@ -109,3 +109,34 @@ def simple_model(assets_dir, name, width, height, **cfg):
     config = Config(**cfg)
     w, v, s = build_viewer_scene(assets_dir, name, width, height, config)
     return _finish(w, v, s)
+
+
+def fibonacci_eye(v, n_total=4096, radius=3.9, center=(0.0, 1.0, 0.0)):
+    """Eye of view v of n_total on a Fibonacci sphere around `center`."""
+    golden = np.pi * (3.0 - np.sqrt(5.0))
+    y = 1.0 - 2.0 * (v + 0.5) / n_total
+    r = np.sqrt(max(0.0, 1.0 - y * y))
+    th = golden * v
+    return (center[0] + radius * r * np.cos(th), center[1] + radius * y, center[2] + radius * r * np.sin(th))
+
+
+def config5_views(assets_dir, name, views, n_total=4096, width=512, height=512, **cfg):
+    """C5: a batch of views of one model (AfricanHead: views 0-2047, Robot: 2048-4095 of 4096), 512x512, no AA.
+
+    FRAME section = every view of `views` back to back (the throughput unit of the render farm); the tail renders each
+    view again and reads it back as color_v<k> / depth_v<k> (parity)."""
+    config = Config(**cfg)
+    w, viewer, scene = build_viewer_scene(assets_dir, name, width, height, config, eye=fibonacci_eye(views[0], n_total))
+    viewer.draw_frame(scene)
+    w.frame_begin()
+    for v in views:
+        viewer.cam_main.look_at(fibonacci_eye(v, n_total), (0, 1, 0), (0, 1, 0))
+        viewer.draw_frame(scene)
+    w.frame_end()
+    for k, v in enumerate(views):
+        viewer.cam_main.look_at(fibonacci_eye(v, n_total), (0, 1, 0), (0, 1, 0))
+        viewer.draw_frame(scene)
+        w.wait_idle()
+        w.readback(viewer.tex_color_main, "color_v%d" % k)
+        w.readback(viewer.tex_depth_main, "depth_v%d" % k)
+    return w

@@ -74,3 +74,31 @@ def build_c1(work_dir, width=1000, height=800, **cfg):
     if not os.path.exists(trace):
         scenes.config1_cube(assets_dir(), width, height, **cfg).save(trace)
     return trace, work_dir
+
+
+def build_c3(work_dir, width=3840, height=2160, **cfg):
+    """C3 = BoomBox + GlassTable, shadow mapping, alpha blending (GlassTable glass), FXAA pass."""
+    os.makedirs(work_dir, exist_ok=True)
+    trace = os.path.join(work_dir, "c3_%dx%d.sglt" % (width, height))
+    if not os.path.exists(trace):
+        scenes.config3_boombox_table(assets_dir(), width, height, **cfg).save(trace)
+    return trace, work_dir
+
+
+def build_c4(work_dir, n_tris=100000, width=1920, height=1080, tex_size=1024, **kw):
+    """C4 = synthetic triangle soup (no assets needed): mixed sizes, 8 mip-mapped REPEAT textures, Blinn-Phong."""
+    from .scene import synth
+    os.makedirs(work_dir, exist_ok=True)
+    trace = os.path.join(work_dir, "c4_%d_%dx%d_t%d.sglt" % (n_tris, width, height, tex_size))
+    if not os.path.exists(trace):
+        synth.soup_trace(n_tris, width, height, tex_size=tex_size, **kw).save(trace)
+    return trace, work_dir
+
+
+def build_c5(work_dir, model, views, n_total=4096, width=512, height=512, **cfg):
+    """C5 = multi-view batch: `views` (indices into the n_total-view Fibonacci sphere) of AfricanHead or Robot."""
+    os.makedirs(work_dir, exist_ok=True)
+    trace = os.path.join(work_dir, "c5_%s_%s_%dx%d.sglt" % (model, "-".join(str(v) for v in views[:6]) + ("+%d" % len(views)), width, height))
+    if not os.path.exists(trace):
+        scenes.config5_views(assets_dir(), model, list(views), n_total, width, height, **cfg).save(trace)
+    return trace, work_dir
