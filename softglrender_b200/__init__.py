@@ -15,6 +15,7 @@ import os
 
 PACKAGE_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PACKAGE_DIR)
-LIB_DIR = os.path.join(PACKAGE_DIR, "lib")
+# SGL_LIB_DIR selects an alternative build of the SAME sources (compile-time A/B variants made by build.py --variant)
+LIB_DIR = os.environ.get("SGL_LIB_DIR") or os.path.join(PACKAGE_DIR, "lib")
 
 __all__ = ["PACKAGE_DIR", "REPO_ROOT", "LIB_DIR"]

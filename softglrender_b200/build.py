@@ -36,7 +36,19 @@ def _run(cmd, log=None):
     return r.stdout
 
 
-def build(force=False, verbose=True):
+def build(force=False, verbose=True, out=None, extra_flags=()):
+    """out / extra_flags: A/B variant of the same sources (e.g. -DSGL_VIS_MIN_BLOCKS=5) into another directory."""
+    global OUT
+    saved = OUT
+    if out:
+        OUT = out
+    try:
+        return _build(force, verbose, list(extra_flags))
+    finally:
+        OUT = saved
+
+
+def _build(force, verbose, extra_flags):
     os.makedirs(OUT, exist_ok=True)
     hdrs = [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
     objs, jobs = [], []
@@ -45,7 +57,7 @@ def build(force=False, verbose=True):
         o = os.path.join(OUT, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _newer(o, [s] + hdrs):
-            jobs.append((["nvcc"] + NVCC_FLAGS + ["-c", s, "-o", o], o + ".ptxas.log"))
+            jobs.append((["nvcc"] + NVCC_FLAGS + extra_flags + ["-c", s, "-o", o], o + ".ptxas.log"))
     if jobs and verbose:
         print("[build] nvcc: %d translation unit(s) for sm_100a ..." % len(jobs), flush=True)
     with ThreadPoolExecutor(max_workers=len(jobs) or 1) as ex:
@@ -77,4 +89,8 @@ def build(force=False, verbose=True):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv)
+    if "--variant" in sys.argv:      # python -m softglrender_b200.build --variant NAME -DFOO=1 ...
+        i = sys.argv.index("--variant")
+        build(force=True, out=os.path.join(HERE, "lib_variants", sys.argv[i + 1]), extra_flags=sys.argv[i + 2:])
+    else:
+        build(force="--force" in sys.argv)

@@ -8,6 +8,9 @@
 #define SGL_MAX_LEVELS 16
 #define SGL_OWNER_NONE 0xFFFFFFFFu
 #define SGL_BIG_PRIM_TILES 64       // primitives touching more tiles than this go to the pass-wide "big" list
+#define SGL_BIG_PER_TILE 32        // room per tile for big primitives in the pre-sorted tile lists
+#define SGL_TILE_UNSORTED 0xFFFFFFFFu
+#define SGL_TILE_CLASSES 4          // list length >= 192, >= 48, >= 12, rest
 #define SGL_RASTER_BLOCK 32         // RendererSoft::rasterBlockSize_ (RendererSoft.h:128)
 
 // texture / attachment descriptor (TextureSoft<T> + ImageBufferSoft<T>, TextureSoft.h:20-255)
@@ -122,6 +125,11 @@ struct SglPassParams {
   uint32_t *tileCursor;         // [tiles]
   uint32_t *binSlots;           // primitive slots per tile (unordered)
   uint32_t binCapacity;
+  uint32_t *tileSorted;         // per tile: slots in submission order (bins + near big primitives), written by
+                                // sglTileSortKernel at tileOffset[t] + t * SGL_BIG_PER_TILE; null = not prepared
+  uint32_t *tileSortedCount;    // [tiles] entries of the sorted list, SGL_TILE_UNSORTED = use the in-kernel gather
+  uint32_t *tileOrder;          // [SGL_TILE_CLASSES][tiles]: tiles by descending list length class (heavy tiles are
+  uint32_t *tileClassCount;     // [SGL_TILE_CLASSES]           launched first so that they cannot become stragglers)
   uint32_t *bigList;            // slots of big primitives
   uint32_t *bigCount;
   uint32_t bigCapacity;

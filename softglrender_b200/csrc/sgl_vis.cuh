@@ -15,6 +15,12 @@
 #define SGL_SORT_CAP 2048
 #endif
 #define SGL_VIS_BATCH 64
+#ifndef SGL_SHADE_MIN_BLOCKS
+#define SGL_SHADE_MIN_BLOCKS 4
+#endif
+#ifndef SGL_VIS_MIN_BLOCKS
+#define SGL_VIS_MIN_BLOCKS 4
+#endif
 
 // conservative "can primitive p write into tile (tx,ty)?" beyond the bbox overlap; MUST be the same function in the
 // counting pass (sglSetupKernel), the fill pass (sglBinFillKernel) and the big-list scan of the tile kernels
@@ -81,6 +87,84 @@ __device__ __forceinline__ void sglSortTileList(uint32_t *keys, uint32_t *vals, 
   sglBitonicSortKV(keys, vals, n2);
 }
 
+// Geometry-stage preparation of the tile lists: gathers a tile's bin plus the big primitives that can touch it, sorts by
+// order key and stores the slots, so that the pixel-stage kernels stream a ready list instead of running the gather /
+// sort latency chain with 256 mostly idle threads per tile.  Tiles whose list does not fit are flagged SGL_TILE_UNSORTED
+// and take the in-kernel path.  grid = tiles, block = 128.  (Compiled into the translation unit that launches it only.)
+#ifdef SGL_WITH_TILE_SORT
+__global__ void __launch_bounds__(128) sglTileSortKernel(SglPassParams P) {
+  __shared__ uint32_t sKeys[SGL_SORT_CAP];
+  __shared__ uint32_t sSlots[SGL_SORT_CAP];
+  __shared__ int sCount, sBig;
+  const int tile = blockIdx.x, tid = threadIdx.x;
+  if (P.tileOwner && P.tileOwner[tile] != P.rank) return;
+  const int tx = tile % P.tilesX, ty = tile / P.tilesX;
+  const uint32_t off = P.tileOffset[tile];
+  uint32_t nList = P.tileOffset[tile + 1] - off;
+  if (off + nList > P.binCapacity) nList = off < P.binCapacity ? P.binCapacity - off : 0;
+  uint32_t nBig = *P.bigCount;
+  if (nBig > P.bigCapacity) nBig = P.bigCapacity;
+  if (nList > SGL_SORT_CAP - SGL_BIG_PER_TILE) {
+    if (tid == 0) {
+      P.tileSortedCount[tile] = SGL_TILE_UNSORTED;
+      P.tileOrder[atomicAdd(&P.tileClassCount[0], 1u)] = (uint32_t) tile;
+    }
+    return;
+  }
+  const int tx0 = tx * SGL_TILE, ty0 = ty * SGL_TILE, tx1 = tx0 + SGL_TILE - 1, ty1 = ty0 + SGL_TILE - 1;
+  if (tid == 0) { sCount = 0; sBig = 0; }
+  __syncthreads();
+  for (uint32_t i = tid; i < nList; i += blockDim.x) {
+    uint32_t slot = P.binSlots[off + i];
+    int idx = atomicAdd(&sCount, 1);
+    sKeys[idx] = P.primKeys[slot];
+    sSlots[idx] = slot;
+  }
+  for (uint32_t i = tid; i < nBig; i += blockDim.x) {
+    uint32_t slot = P.bigList[i];
+    const SglPrim &bp = P.prims[slot];
+    if (bp.bx0 <= tx1 && bp.bx1 >= tx0 && bp.by0 <= ty1 && bp.by1 >= ty0 && sglPrimNearTile(bp, tx, ty)) {
+      if (atomicAdd(&sBig, 1) < SGL_BIG_PER_TILE) {
+        int idx = atomicAdd(&sCount, 1);
+        sKeys[idx] = P.primKeys[slot];
+        sSlots[idx] = slot;
+      }
+    }
+  }
+  __syncthreads();
+  if (sBig > SGL_BIG_PER_TILE) {
+    if (tid == 0) {
+      P.tileSortedCount[tile] = SGL_TILE_UNSORTED;
+      P.tileOrder[atomicAdd(&P.tileClassCount[0], 1u)] = (uint32_t) tile;
+    }
+    return;
+  }
+  const int n = sCount;
+  sglSortTileList(sKeys, sSlots, n);
+  __syncthreads();
+  uint32_t *dst = P.tileSorted + off + (size_t) tile * SGL_BIG_PER_TILE;
+  for (int i = tid; i < n; i += blockDim.x) dst[i] = sSlots[i];
+  if (tid == 0) {
+    P.tileSortedCount[tile] = (uint32_t) n;
+    const int cls = n >= 192 ? 0 : (n >= 48 ? 1 : (n >= 12 ? 2 : 3));
+    P.tileOrder[(size_t) cls * (P.tilesX * P.tilesY) + atomicAdd(&P.tileClassCount[cls], 1u)] = (uint32_t) tile;
+  }
+}
+#endif  // SGL_WITH_TILE_SORT
+
+// blockIdx -> tile through the class lists of sglTileSortKernel (heaviest class first); -1 = nothing to do
+__device__ __forceinline__ int sglTileOfBlock(const SglPassParams &P, int block) {
+  if (!P.tileOrder) return (P.tileOwner && P.tileOwner[block] != P.rank) ? -1 : block;
+  uint32_t b = (uint32_t) block;
+#pragma unroll
+  for (int c = 0; c < SGL_TILE_CLASSES; c++) {
+    const uint32_t n = P.tileClassCount[c];
+    if (b < n) return (int) P.tileOrder[(size_t) c * (P.tilesX * P.tilesY) + b];
+    b -= n;
+  }
+  return -1;   // tiles of other ranks are in no class
+}
+
 // one primitive against one pixel: coverage + depth, owners instead of colours
 template<int NS>
 __device__ __forceinline__ void sglVisPixelPrim(const SglPassParams &P, const SglVisPrim &vp, uint32_t slot, int px, int py,
@@ -128,14 +212,14 @@ __device__ __forceinline__ void sglVisPixelPrim(const SglPassParams &P, const Sg
 }
 
 template<int NS>
-__global__ void __launch_bounds__(SGL_TILE_THREADS, 4) sglVisKernel(SglPassParams P) {
+__global__ void __launch_bounds__(SGL_TILE_THREADS, SGL_VIS_MIN_BLOCKS) sglVisKernel(SglPassParams P) {
   __shared__ uint32_t sKeys[SGL_SORT_CAP];
   __shared__ uint32_t sSlots[SGL_SORT_CAP];
   __shared__ SglVisPrim sPrims[SGL_VIS_BATCH];
   __shared__ int sCount;
 
-  const int tile = blockIdx.x;
-  if (P.tileOwner && P.tileOwner[tile] != P.rank) return;
+  const int tile = sglTileOfBlock(P, blockIdx.x);
+  if (tile < 0) return;
   const int tx = tile % P.tilesX, ty = tile / P.tilesX;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // a warp owns an 8x4 pixel block of the tile (same mapping as the shading kernel): small triangles then concern one
@@ -159,12 +243,69 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS, 4) sglVisKernel(SglPassParam
   }
 
   const uint32_t off = P.tileOffset[tile];
+
+  // one batch of <= SGL_VIS_BATCH records whose slots sit in slots[0..nb): stage the records in shared memory, derive the
+  // edge constants, cull per warp, then every pixel visits the survivors in order
+  auto runBatch = [&](const uint32_t *slots, int nb) {
+    {  // 64 records x 4 x uint4 = one 16-byte load per thread, then one thread per record derives the edge constants
+      const int r = tid >> 2, q = tid & 3;
+      if (r < nb) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.prims + slots[r]);
+        reinterpret_cast<uint4 *>(&sPrims[r].p)[q] = __ldg(src + q);
+      }
+    }
+    __syncthreads();
+    if (tid < nb && (sPrims[tid].p.flags & SGL_PF_KIND_MASK) == SGL_PK_TRIANGLE) sPrims[tid].e = sglTriEdge(sPrims[tid].p);
+    __syncthreads();
+    // warp-level cull: each lane tests two records of the batch against the warp's 8x4 block (bbox, then the same
+    // conservative outside test the pixels use, over the block's sample positions); the warp then visits only the
+    // surviving records, in order
+    uint32_t rel[2];
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+      const int idx = hh * 32 + lane;
+      bool r = false;
+      if (idx < nb) {
+        const SglVisPrim &vp = sPrims[idx];
+        r = vp.p.bx0 <= wbx + 7 && vp.p.bx1 >= wbx && vp.p.by0 <= wby + 3 && vp.p.by1 >= wby;
+        if (r) {
+          const uint32_t kind = vp.p.flags & SGL_PF_KIND_MASK;
+          if (kind == SGL_PK_TRIANGLE) r = !sglTriSurelyOutside(vp.e, (float) wbx + 4.f, (float) wby + 2.f, 3.875f, 1.875f);
+          else if (kind == SGL_PK_LINE) r = sglLineNearRect(vp.p, wbx, wby, wbx + 7, wby + 3);
+        }
+      }
+      rel[hh] = __ballot_sync(0xffffffffu, r);
+    }
+    if (inFb) {
+#pragma unroll
+      for (int hh = 0; hh < 2; hh++) {
+        uint32_t m = rel[hh];
+        while (m) {
+          const int k = hh * 32 + __ffs(m) - 1;
+          m &= m - 1;
+          sglVisPixelPrim<NS>(P, sPrims[k], slots[k], px, py, depth, owner, hasColor, hasDepth);
+        }
+      }
+    }
+  };
+
+  const uint32_t pre = P.tileSortedCount ? P.tileSortedCount[tile] : SGL_TILE_UNSORTED;
+  if (pre != SGL_TILE_UNSORTED) {
+    // list prepared by sglTileSortKernel: stream it
+    const uint32_t *list = P.tileSorted + off + (size_t) tile * SGL_BIG_PER_TILE;
+    for (uint32_t b0 = 0; b0 < pre; b0 += SGL_VIS_BATCH) {
+      const int nb = pre - b0 < SGL_VIS_BATCH ? (int) (pre - b0) : SGL_VIS_BATCH;
+      __syncthreads();
+      if (tid < nb) sSlots[tid] = __ldg(list + b0 + tid);
+      __syncthreads();
+      runBatch(sSlots, nb);
+    }
+  } else {
   uint32_t nList = P.tileOffset[tile + 1] - off;
   if (off + nList > P.binCapacity) nList = off < P.binCapacity ? P.binCapacity - off : 0;
   uint32_t nBig = *P.bigCount;
   if (nBig > P.bigCapacity) nBig = P.bigCapacity;
   const int tx0 = tx * SGL_TILE, ty0 = ty * SGL_TILE, tx1 = tx0 + SGL_TILE - 1, ty1 = ty0 + SGL_TILE - 1;
-
   // key windows: the common case (everything fits) is one window covering all keys
   uint32_t lo = 0;
   const uint32_t keyEnd = 0xFFFFFFFFu;
@@ -203,50 +344,12 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS, 4) sglVisKernel(SglPassParam
     for (int b0 = 0; b0 < n; b0 += SGL_VIS_BATCH) {   // process in order
       const int nb = n - b0 < SGL_VIS_BATCH ? n - b0 : SGL_VIS_BATCH;
       __syncthreads();
-      {  // 64 records x 4 x uint4 = one 16-byte load per thread, then one thread per record derives the edge constants
-        const int r = tid >> 2, q = tid & 3;
-        if (r < nb) {
-          const uint4 *src = reinterpret_cast<const uint4 *>(P.prims + sSlots[b0 + r]);
-          reinterpret_cast<uint4 *>(&sPrims[r].p)[q] = __ldg(src + q);
-        }
-      }
-      __syncthreads();
-      if (tid < nb && (sPrims[tid].p.flags & SGL_PF_KIND_MASK) == SGL_PK_TRIANGLE) sPrims[tid].e = sglTriEdge(sPrims[tid].p);
-      __syncthreads();
-      // warp-level cull: each lane tests two records of the batch against the warp's 8x4 block (bbox, then the same
-      // conservative outside test the pixels use, over the block's sample positions); the warp then visits only the
-      // surviving records, in order
-      uint32_t rel[2];
-#pragma unroll
-      for (int hh = 0; hh < 2; hh++) {
-        const int idx = hh * 32 + lane;
-        bool r = false;
-        if (idx < nb) {
-          const SglVisPrim &vp = sPrims[idx];
-          r = vp.p.bx0 <= wbx + 7 && vp.p.bx1 >= wbx && vp.p.by0 <= wby + 3 && vp.p.by1 >= wby;
-          if (r) {
-            const uint32_t kind = vp.p.flags & SGL_PF_KIND_MASK;
-            if (kind == SGL_PK_TRIANGLE) r = !sglTriSurelyOutside(vp.e, (float) wbx + 4.f, (float) wby + 2.f, 3.875f, 1.875f);
-            else if (kind == SGL_PK_LINE) r = sglLineNearRect(vp.p, wbx, wby, wbx + 7, wby + 3);
-          }
-        }
-        rel[hh] = __ballot_sync(0xffffffffu, r);
-      }
-      if (inFb) {
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-          uint32_t m = rel[hh];
-          while (m) {
-            const int k = hh * 32 + __ffs(m) - 1;
-            m &= m - 1;
-            sglVisPixelPrim<NS>(P, sPrims[k], sSlots[b0 + k], px, py, depth, owner, hasColor, hasDepth);
-          }
-        }
-      }
+      runBatch(sSlots + b0, nb);
     }
     __syncthreads();
     if (fits || hi == keyEnd) break;
     lo = hi;
+  }
   }
 
   if (inFb) {
@@ -266,7 +369,7 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS, 4) sglVisKernel(SglPassParam
 // ---------------------------------------------------------------------------------------------------------
 // grid = tiles (same ownership rule as the visibility kernel); a warp shades an 8x4 pixel block
 template<int NS>
-__global__ void __launch_bounds__(SGL_TILE_THREADS) sglShadeKernel(SglPassParams P) {
+__global__ void __launch_bounds__(SGL_TILE_THREADS, SGL_SHADE_MIN_BLOCKS) sglShadeKernel(SglPassParams P) {
   const int tile = blockIdx.x;
   if (P.tileOwner && P.tileOwner[tile] != P.rank) return;
   const int tx = tile % P.tilesX, ty = tile / P.tilesX;

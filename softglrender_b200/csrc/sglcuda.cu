@@ -3,6 +3,7 @@
 // snapshots of uniforms/sampler bindings/states, laying out the pass' transient arena in HBM, and launching
 // the five kernels of sgl_kernels.cuh at sgl_pass_end (tile-based deferred execution, the model the reference's
 // own Vulkan backend uses behind the same API -- Render/Vulkan/RendererVulkan.cpp:73-205).
+#define SGL_WITH_TILE_SORT
 #include "sgl_kernels.cuh"
 
 #include <algorithm>
@@ -837,6 +838,7 @@ int sgl_pass_end(void) {
   size_t oBigCount = take(sizeof(uint32_t));
   size_t oTileCount = take(sizeof(uint32_t) * nTiles);
   size_t oTileCursor = take(sizeof(uint32_t) * nTiles);
+  size_t oTileClassCount = take(sizeof(uint32_t) * SGL_TILE_CLASSES);
   size_t zeroBytes = off - oZero;
   size_t oTileOffset = take(sizeof(uint32_t) * (nTiles + 1));
   int primSlots = 0, keyBase = 0, maxVerts = 0, maxPrims = 0, maxSlots = 0;
@@ -877,6 +879,10 @@ int sgl_pass_end(void) {
   // depth-only path: the region holds 64-byte work items instead (>= 2 per primitive slot + one per 512 framebuffer pixels)
   if (depthOnly) binCapacity = ((size_t) primSlots * 2 + (size_t) fbW * fbH / 512 + 65536) * (sizeof(SglPrim) / sizeof(uint32_t));
   size_t oBins = take(sizeof(uint32_t) * binCapacity);
+  // pre-sorted tile lists (sglTileSortKernel): bins + room for SGL_BIG_PER_TILE big primitives per tile
+  size_t oTileSorted = depthOnly ? 0 : take(sizeof(uint32_t) * (binCapacity + (size_t) nTiles * SGL_BIG_PER_TILE));
+  size_t oTileSortedCount = depthOnly ? 0 : take(sizeof(uint32_t) * nTiles);
+  size_t oTileOrder = depthOnly ? 0 : take(sizeof(uint32_t) * nTiles * SGL_TILE_CLASSES);
   Ctx::Arena &arena = g.arenas[g.arenaNext];
   g.arenaNext = (g.arenaNext + 1) % 3;
   int rc = ensureArena(arena, off);
@@ -956,6 +962,10 @@ int sgl_pass_end(void) {
   P.tileCursor = (uint32_t *) (A + oTileCursor);
   P.binSlots = (uint32_t *) (A + oBins);
   P.binCapacity = (uint32_t) binCapacity;
+  P.tileSorted = depthOnly ? nullptr : (uint32_t *) (A + oTileSorted);
+  P.tileSortedCount = depthOnly ? nullptr : (uint32_t *) (A + oTileSortedCount);
+  P.tileOrder = depthOnly ? nullptr : (uint32_t *) (A + oTileOrder);
+  P.tileClassCount = (uint32_t *) (A + oTileClassCount);
   P.bigList = (uint32_t *) (A + oBigList);
   P.bigCount = (uint32_t *) (A + oBigCount);
   P.bigCapacity = (uint32_t) std::max(primSlots, 1);
@@ -1024,6 +1034,8 @@ int sgl_pass_end(void) {
     rc = launch("sglBinFillKernel", sglBinFillKernel, dim3((maxSlots + 255) / 256, nDraws), dim3(256), P);
     if (rc) return rc;
   }
+  rc = launch("sglTileSortKernel", sglTileSortKernel, dim3(nTiles), dim3(128), P);
+  if (rc) return rc;
   rc = toPixelStage();
   if (rc) return rc;
   // Deferred (visibility + shading) path for passes made of opaque draws whose point/line programs have no varyings;

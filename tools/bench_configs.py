@@ -43,6 +43,13 @@ def main():
         for _ in range(3):
             p.frame(sync=False)
         capi.check(lib.sgl_wait_idle())
+        import time
+        h0 = time.perf_counter()
+        burst = 4 if units > 1 else 8
+        for _ in range(burst):
+            p.frame(sync=False)
+        host_ms = (time.perf_counter() - h0) * 1e3 / burst
+        capi.check(lib.sgl_wait_idle())
         capi.check(lib.sgl_reset_counters())
         ms = C.c_float()
         capi.check(lib.sgl_timer_begin())
@@ -58,7 +65,7 @@ def main():
         capi.check(lib.sgl_set_profiling(0))
         p.close()
         r = {"workload": name, "units_per_s": units * steps / (ms.value / 1e3), "unit": "views/s" if key == "c5" else "frames/s",
-             "ms_per_step": ms.value / steps, "fragments_per_step": ctr["fragments_shaded"] / steps,
+             "ms_per_step": ms.value / steps, "host_submit_ms_per_step": host_ms, "fragments_per_step": ctr["fragments_shaded"] / steps,
              "gfrag_per_s": ctr["fragments_shaded"] / (ms.value / 1e3) / 1e9, "primitives_per_step": ctr["primitives_in"] / steps,
              "clip_overflow": ctr["clip_overflow"], "kernel_ms_per_step": {k: v[1] / 3.0 for k, v in sorted(kt.items())}}
         if args.cpu and os.path.exists(workloads.REF_PLAYER) and key != "c4big":
