@@ -121,6 +121,12 @@ typedef struct SglKernelTime {
   uint64_t launches;
   double total_ms;
 } SglKernelTime;
+/* per-tile primitive list lengths of the most recent colour pass (row-major tiles; 0xFFFFFFFF = list overflowed into the
+ * in-kernel path) -- load-balance instrumentation */
+int sgl_get_tile_list_sizes(uint32_t *out, int capacity, int *tiles_x_out, int *tiles_y_out);
+/* enable != 0: the visibility kernel of later colour passes records per-tile start/end times (globaltimer ns);
+ * out (may be NULL) receives [tiles][2] of the most recent such pass */
+int sgl_debug_tile_times(int enable, unsigned long long *out, int capacity_tiles);
 int sgl_set_profiling(int on);
 int sgl_get_kernel_times(SglKernelTime *out, int capacity);   /* returns the number of entries written */
 

@@ -49,6 +49,7 @@ class SglKernelTime(C.Structure):
 C_ABI_SYMBOLS = [
     "sgl_init", "sgl_shutdown", "sgl_last_error", "sgl_set_stream", "sgl_wait_idle", "sgl_get_counters",
     "sgl_reset_counters", "sgl_timer_begin", "sgl_timer_end", "sgl_set_profiling", "sgl_get_kernel_times",
+    "sgl_get_tile_list_sizes", "sgl_debug_tile_times",
     "sgl_shader_uniform_offset", "sgl_shader_sampler_slot",
     "sgl_shader_define_bit", "sgl_shader_uniform_size", "sgl_shader_varying_floats", "sgl_buffer_create",
     "sgl_buffer_upload", "sgl_buffer_destroy", "sgl_texture_create", "sgl_texture_destroy", "sgl_texture_upload",
@@ -109,6 +110,8 @@ def load():
     _lib.sgl_kat_sample.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     _lib.sgl_kat_blend.argtypes = [C.POINTER(SglRenderStates), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     _lib.sgl_kat_depth.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    _lib.sgl_get_tile_list_sizes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    _lib.sgl_debug_tile_times.argtypes = [C.c_int, C.c_void_p, C.c_int]
     _lib.sgl_get_kernel_times.argtypes = [C.POINTER(SglKernelTime), C.c_int]
     return _lib
 

@@ -101,11 +101,16 @@ __global__ void __launch_bounds__(128) sglSetupKernel(const SglDrawRec *draws, S
 }
 
 // single CTA: tileOffset = exclusive scan(tileCount); tileOffset[nTiles] = total (clamped entries are dropped later)
+// Also classifies the tiles by bin length (heavy first: SglPassParams::tileOrder) and marks every tile's pre-sorted list
+// as absent; sglTileSortKernel then prepares the lists of the heavy classes only.
 __global__ void __launch_bounds__(1024) sglTileScanKernel(const uint32_t *tileCount, uint32_t *tileOffset, int nTiles,
-                                                         unsigned long long *counters) {
+                                                         unsigned long long *counters, uint32_t *tileOrder, uint32_t *tileClassCount,
+                                                         uint32_t *tileSortedCount, const uint8_t *tileOwner, int rank) {
   __shared__ uint32_t sWarp[32];
   __shared__ uint32_t sCarry;
+  __shared__ uint32_t sClass[SGL_TILE_CLASSES];   // this CTA is the only writer of the class lists
   if (threadIdx.x == 0) sCarry = 0;
+  if (threadIdx.x < SGL_TILE_CLASSES) sClass[threadIdx.x] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int base = 0; base < nTiles; base += 1024) {
@@ -132,7 +137,14 @@ __global__ void __launch_bounds__(1024) sglTileScanKernel(const uint32_t *tileCo
     __syncthreads();
     uint32_t carry = sCarry;
     uint32_t excl = carry + sWarp[warp] + inc - v;
-    if (i < nTiles) tileOffset[i] = excl;
+    if (i < nTiles) {
+      tileOffset[i] = excl;
+      if (tileOrder && !(tileOwner && tileOwner[i] != rank)) {
+        tileSortedCount[i] = SGL_TILE_UNSORTED;
+        const int cls = v >= 184u ? 0 : (v >= 40u ? 1 : (v >= 8u ? 2 : 3));
+        tileOrder[(size_t) cls * nTiles + atomicAdd(&sClass[cls], 1u)] = (uint32_t) i;
+      }
+    }
     __syncthreads();
     if (threadIdx.x == 1023) sCarry = excl + v;
     __syncthreads();
@@ -141,6 +153,7 @@ __global__ void __launch_bounds__(1024) sglTileScanKernel(const uint32_t *tileCo
     tileOffset[nTiles] = sCarry;
     atomicAdd(counters + 3, (unsigned long long) sCarry);
   }
+  if (tileOrder && threadIdx.x < SGL_TILE_CLASSES) tileClassCount[threadIdx.x] = sClass[threadIdx.x];
 }
 
 // grid = (ceil(maxSlotsPerDraw/256), drawCount): one thread per primitive slot (originals, then appended)
@@ -418,7 +431,9 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS) sglTilePackKernel(uint32_t *
 __global__ void __launch_bounds__(1024) sglTileOwnerPrefixKernel(const uint8_t *owner, uint32_t *prefix, int nTiles, int rank) {
   __shared__ uint32_t sWarp[32];
   __shared__ uint32_t sCarry;
+  __shared__ uint32_t sClass[SGL_TILE_CLASSES];   // this CTA is the only writer of the class lists
   if (threadIdx.x == 0) sCarry = 0;
+  if (threadIdx.x < SGL_TILE_CLASSES) sClass[threadIdx.x] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int base = 0; base < nTiles; base += 1024) {

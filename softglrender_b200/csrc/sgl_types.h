@@ -130,9 +130,11 @@ struct SglPassParams {
   uint32_t *tileSortedCount;    // [tiles] entries of the sorted list, SGL_TILE_UNSORTED = use the in-kernel gather
   uint32_t *tileOrder;          // [SGL_TILE_CLASSES][tiles]: tiles by descending list length class (heavy tiles are
   uint32_t *tileClassCount;     // [SGL_TILE_CLASSES]           launched first so that they cannot become stragglers)
+  int32_t splitCap;             // MSAA visibility kernel: up to splitCap heavy tiles run as four quarter-tile CTAs
   uint32_t *bigList;            // slots of big primitives
   uint32_t *bigCount;
   uint32_t bigCapacity;
   const SglTexObj *textures;
   unsigned long long *counters; // device-side SglCounters mirror
+  unsigned long long *tileTimes; // instrumentation (normally null): [tiles][2] globaltimer ns at CTA start / end of the visibility kernel
 };

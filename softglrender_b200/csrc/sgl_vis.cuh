@@ -92,77 +92,150 @@ __device__ __forceinline__ void sglSortTileList(uint32_t *keys, uint32_t *vals, 
 // sort latency chain with 256 mostly idle threads per tile.  Tiles whose list does not fit are flagged SGL_TILE_UNSORTED
 // and take the in-kernel path.  grid = tiles, block = 128.  (Compiled into the translation unit that launches it only.)
 #ifdef SGL_WITH_TILE_SORT
-__global__ void __launch_bounds__(128) sglTileSortKernel(SglPassParams P) {
-  __shared__ uint32_t sKeys[SGL_SORT_CAP];
-  __shared__ uint32_t sSlots[SGL_SORT_CAP];
-  __shared__ int sCount, sBig;
-  const int tile = blockIdx.x, tid = threadIdx.x;
-  if (P.tileOwner && P.tileOwner[tile] != P.rank) return;
+#define SGL_TILE_SORT_WARPS 8
+#define SGL_TILE_SORT_CAP 512     // longest list a warp sorts; longer ones are flagged SGL_TILE_UNSORTED
+// one WARP per heavy tile: grid = ceil(splitCap / 8), block = 256
+__global__ void __launch_bounds__(32 * SGL_TILE_SORT_WARPS) sglTileSortKernel(SglPassParams P) {
+  __shared__ uint32_t sKeys[SGL_TILE_SORT_WARPS][SGL_TILE_SORT_CAP];
+  __shared__ uint32_t sSlots[SGL_TILE_SORT_WARPS][SGL_TILE_SORT_CAP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nTiles = P.tilesX * P.tilesY;
+  // only the heavy classes (0 and 1 of sglTileScanKernel) get a prepared list: they are the tiles the visibility kernel
+  // splits into quarter-tile CTAs; light tiles keep the in-kernel gather (thousands of them hide each other's latency)
+  const uint32_t h = (uint32_t) (blockIdx.x * SGL_TILE_SORT_WARPS + warp);
+  const uint32_t c0 = P.tileClassCount[0], c1 = P.tileClassCount[1];
+  if (h >= c0 + c1) return;
+  const int tile = (int) (h < c0 ? P.tileOrder[h] : P.tileOrder[(size_t) nTiles + (h - c0)]);
+  uint32_t *keys = sKeys[warp], *slots = sSlots[warp];
   const int tx = tile % P.tilesX, ty = tile / P.tilesX;
   const uint32_t off = P.tileOffset[tile];
   uint32_t nList = P.tileOffset[tile + 1] - off;
   if (off + nList > P.binCapacity) nList = off < P.binCapacity ? P.binCapacity - off : 0;
   uint32_t nBig = *P.bigCount;
   if (nBig > P.bigCapacity) nBig = P.bigCapacity;
-  if (nList > SGL_SORT_CAP - SGL_BIG_PER_TILE) {
-    if (tid == 0) {
-      P.tileSortedCount[tile] = SGL_TILE_UNSORTED;
-      P.tileOrder[atomicAdd(&P.tileClassCount[0], 1u)] = (uint32_t) tile;
+  bool fits = nList <= SGL_TILE_SORT_CAP - SGL_BIG_PER_TILE;
+  int n = 0;
+  if (fits) {
+    for (uint32_t i = lane; i < nList; i += 32) {
+      const uint32_t slot = P.binSlots[off + i];
+      keys[i] = P.primKeys[slot];
+      slots[i] = slot;
     }
-    return;
-  }
-  const int tx0 = tx * SGL_TILE, ty0 = ty * SGL_TILE, tx1 = tx0 + SGL_TILE - 1, ty1 = ty0 + SGL_TILE - 1;
-  if (tid == 0) { sCount = 0; sBig = 0; }
-  __syncthreads();
-  for (uint32_t i = tid; i < nList; i += blockDim.x) {
-    uint32_t slot = P.binSlots[off + i];
-    int idx = atomicAdd(&sCount, 1);
-    sKeys[idx] = P.primKeys[slot];
-    sSlots[idx] = slot;
-  }
-  for (uint32_t i = tid; i < nBig; i += blockDim.x) {
-    uint32_t slot = P.bigList[i];
-    const SglPrim &bp = P.prims[slot];
-    if (bp.bx0 <= tx1 && bp.bx1 >= tx0 && bp.by0 <= ty1 && bp.by1 >= ty0 && sglPrimNearTile(bp, tx, ty)) {
-      if (atomicAdd(&sBig, 1) < SGL_BIG_PER_TILE) {
-        int idx = atomicAdd(&sCount, 1);
-        sKeys[idx] = P.primKeys[slot];
-        sSlots[idx] = slot;
+    n = (int) nList;
+    const int tx0 = tx * SGL_TILE, ty0 = ty * SGL_TILE, tx1 = tx0 + SGL_TILE - 1, ty1 = ty0 + SGL_TILE - 1;
+    int big = 0;
+    for (uint32_t i0 = 0; i0 < nBig; i0 += 32) {      // warp-uniform trip count
+      const uint32_t i = i0 + lane;
+      bool near = false;
+      uint32_t slot = 0;
+      if (i < nBig) {
+        slot = P.bigList[i];
+        const SglPrim &bp = P.prims[slot];
+        near = bp.bx0 <= tx1 && bp.bx1 >= tx0 && bp.by0 <= ty1 && bp.by1 >= ty0 && sglPrimNearTile(bp, tx, ty);
       }
+      const uint32_t m = __ballot_sync(0xffffffffu, near);
+      const int pos = big + __popc(m & ((1u << lane) - 1u));
+      if (near && pos < SGL_BIG_PER_TILE) {
+        keys[n + pos] = P.primKeys[slot];
+        slots[n + pos] = slot;
+      }
+      big += __popc(m);
     }
+    if (big > SGL_BIG_PER_TILE) fits = false;
+    n += big;
   }
-  __syncthreads();
-  if (sBig > SGL_BIG_PER_TILE) {
-    if (tid == 0) {
-      P.tileSortedCount[tile] = SGL_TILE_UNSORTED;
-      P.tileOrder[atomicAdd(&P.tileClassCount[0], 1u)] = (uint32_t) tile;
-    }
-    return;
-  }
-  const int n = sCount;
-  sglSortTileList(sKeys, sSlots, n);
-  __syncthreads();
+  if (!fits) return;   // stays SGL_TILE_UNSORTED
+  __syncwarp();
+  // rank sort (keys are unique): each lane ranks its elements against the whole list, then scatters to global memory
   uint32_t *dst = P.tileSorted + off + (size_t) tile * SGL_BIG_PER_TILE;
-  for (int i = tid; i < n; i += blockDim.x) dst[i] = sSlots[i];
-  if (tid == 0) {
-    P.tileSortedCount[tile] = (uint32_t) n;
-    const int cls = n >= 192 ? 0 : (n >= 48 ? 1 : (n >= 12 ? 2 : 3));
-    P.tileOrder[(size_t) cls * (P.tilesX * P.tilesY) + atomicAdd(&P.tileClassCount[cls], 1u)] = (uint32_t) tile;
+  for (int i = lane; i < n; i += 32) {
+    const uint32_t k = keys[i];
+    int rank = 0;
+    for (int j = 0; j < n; j++) rank += keys[j] < k ? 1 : 0;
+    dst[rank] = slots[i];
   }
+  if (lane == 0) P.tileSortedCount[tile] = (uint32_t) n;
 }
 #endif  // SGL_WITH_TILE_SORT
 
-// blockIdx -> tile through the class lists of sglTileSortKernel (heaviest class first); -1 = nothing to do
-__device__ __forceinline__ int sglTileOfBlock(const SglPassParams &P, int block) {
+// blockIdx -> tile through the class lists of sglTileSortKernel (heaviest class first); -1 = nothing to do.
+// With `splitCap` > 0 (MSAA visibility kernel) the first min(heavy, splitCap) tiles of classes 0-1 occupy FOUR blocks
+// each: block b -> tile b / 4, quarter b % 4 (an 8x8 pixel quarter processed with one SAMPLE per lane); quarter = -1
+// means "whole tile, one pixel per lane".
+__device__ __forceinline__ int sglTileOfBlock(const SglPassParams &P, int block, int splitCap, int &quarter) {
+  quarter = -1;
   if (!P.tileOrder) return (P.tileOwner && P.tileOwner[block] != P.rank) ? -1 : block;
+  const size_t nTiles = (size_t) P.tilesX * P.tilesY;
+  uint32_t cnt[SGL_TILE_CLASSES];
+#pragma unroll
+  for (int c = 0; c < SGL_TILE_CLASSES; c++) cnt[c] = P.tileClassCount[c];
   uint32_t b = (uint32_t) block;
+  if (splitCap > 0) {
+    uint32_t heavy = cnt[0] + cnt[1];
+    if (heavy > (uint32_t) splitCap) heavy = (uint32_t) splitCap;
+    if (b < 4u * heavy) {
+      const uint32_t h = b >> 2;
+      quarter = (int) (b & 3u);
+      return (int) (h < cnt[0] ? P.tileOrder[h] : P.tileOrder[nTiles + (h - cnt[0])]);
+    }
+    b = b - 4u * heavy + heavy;      // position in the concatenated class lists, past the split tiles
+  }
 #pragma unroll
   for (int c = 0; c < SGL_TILE_CLASSES; c++) {
-    const uint32_t n = P.tileClassCount[c];
-    if (b < n) return (int) P.tileOrder[(size_t) c * (P.tilesX * P.tilesY) + b];
-    b -= n;
+    if (b < cnt[c]) return (int) P.tileOrder[(size_t) c * nTiles + b];
+    b -= cnt[c];
   }
   return -1;   // tiles of other ranks are in no class
+}
+
+// Sample-per-lane form of sglVisPixelPrim for the quarters of heavy MSAA tiles: the four lanes of a pixel each own one
+// sample (depth + owner in one register each); geometric coverage of the pixel is exchanged with a ballot.  Same
+// arithmetic as sglCoverTriangle / sglVisPixelPrim, evaluated per sample.  Must be called by all 32 lanes.
+__device__ __forceinline__ void sglVisSamplePrim(const SglPassParams &P, const SglVisPrim &vp, uint32_t slot, int px, int py, int s,
+                                                 int lane, bool inFb, float &depth, uint32_t &owner, bool hasColor, bool hasDepth) {
+  const SglPrim &p = vp.p;
+  const uint32_t flags = p.flags;
+  const uint32_t kind = flags & SGL_PF_KIND_MASK;
+  bool cand = inFb && !(px < p.bx0 || px > p.bx1 || py < p.by0 || py > p.by1);
+  if (kind == SGL_PK_TRIANGLE) {   // warp-uniform
+    if (cand && (flags & SGL_PF_IRREGULAR)) {
+      const SglDrawRec &d = P.draws[p.draw];
+      int q;
+      if (!sglAxisVisitedExact(min3f(p.v[0][0], p.v[1][0], p.v[2][0]), max3f(p.v[0][0], p.v[1][0], p.v[2][0]), d.vpW, px, q)) cand = false;
+      else if (!sglAxisVisitedExact(min3f(p.v[0][1], p.v[1][1], p.v[2][1]), max3f(p.v[0][1], p.v[1][1], p.v[2][1]), d.vpH, py, q)) cand = false;
+    }
+    const float fx = (float) px, fy = (float) py;
+    if (cand && sglTriSurelyOutside(vp.e, fx + 0.5f, fy + 0.5f, 0.375f, 0.375f)) cand = false;
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    bool in = false;
+    if (cand) {
+      float ox, oy;
+      sglSampleOffset(4, s, ox, oy);
+      in = sglBarycentric(vp.e, xadd(ox, fx), xadd(oy, fy), b0, b1, b2);
+    }
+    const uint32_t g4 = (__ballot_sync(0xffffffffu, in) >> (lane & 28)) & 0xFu;   // geometric coverage of this pixel
+    if (g4 == 0 || !in) return;
+    float c0, c1, c2;
+    const int shadeIdx = sglBarycentric(vp.e, xadd(fx, 0.5f), xadd(fy, 0.5f), c0, c1, c2) ? 4 : (__ffs(g4) - 1);
+    float z = sglInterpZ(p, 2, b0, b1, b2);
+    if (z < 0.f || z > 1.f) return;                    // depth-range clipping (multisample path)
+    z = gclamp(z, 0.f, 1.f);
+    if (flags & SGL_PF_DEPTH_TEST) {
+      if (!hasDepth) return;
+      if (!sglDepthTest(z, depth, (flags >> SGL_PF_DEPTH_FUNC_SHIFT) & 7)) return;
+      if (flags & SGL_PF_DEPTH_MASK) depth = z;
+    }
+    owner = sglOwner(slot, shadeIdx);
+    return;
+  }
+  if (!hasColor || !cand) return;
+  SglPixelState<1> st;
+  st.depth[0] = depth;
+  uint32_t wrote = 0;
+  if (kind == SGL_PK_POINT) wrote = sglFlatDepth<1>(p, p.v[0][2], hasDepth, st);
+  else sglLineVisit(p, px, py, [&](float, float, float z) { wrote |= sglFlatDepth<1>(p, z, hasDepth, st); });
+  depth = st.depth[0];
+  if (wrote & 1u) owner = sglOwner(slot, 0);
 }
 
 // one primitive against one pixel: coverage + depth, owners instead of colours
@@ -218,10 +291,86 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS, SGL_VIS_MIN_BLOCKS) sglVisKe
   __shared__ SglVisPrim sPrims[SGL_VIS_BATCH];
   __shared__ int sCount;
 
-  const int tile = sglTileOfBlock(P, blockIdx.x);
+  int quarter;
+  const int tile = sglTileOfBlock(P, blockIdx.x, NS == 4 ? P.splitCap : 0, quarter);
   if (tile < 0) return;
   const int tx = tile % P.tilesX, ty = tile / P.tilesX;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (P.tileTimes && tid == 0 && quarter <= 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    P.tileTimes[2 * tile] = t;
+  }
+  if (NS == 4 && quarter >= 0) {
+    const uint32_t pre = P.tileSortedCount[tile];
+    if (pre == SGL_TILE_UNSORTED) {
+      if (quarter != 0) return;       // list not prepared: quarter 0 takes the whole tile below
+    } else {
+      // ---- heavy tile, one 8x8 pixel quarter per CTA, one SAMPLE per lane: a warp owns a 4x2 pixel block
+      const int wbx = tx * SGL_TILE + (quarter & 1) * 8 + (warp & 1) * 4, wby = ty * SGL_TILE + (quarter >> 1) * 8 + (warp >> 1) * 2;
+      const int px = wbx + ((lane >> 2) & 3), py = wby + (lane >> 4), smp = lane & 3;
+      const bool inFb = px < P.fbW && py < P.fbH;
+      const bool hasColor = P.colorBase != nullptr, hasDepth = P.depthBase != nullptr;
+      const size_t idx = ((size_t) py * P.fbW + px) * 4 + smp;
+      float depth = P.clearDepth;
+      uint32_t owner = SGL_OWNER_NONE;
+      if (inFb && hasDepth && !P.clearDepthFlag) depth = P.depthBase[idx];
+      const uint32_t *list = P.tileSorted + P.tileOffset[tile] + (size_t) tile * SGL_BIG_PER_TILE;
+      for (uint32_t b0 = 0; b0 < pre; b0 += SGL_VIS_BATCH) {
+        const int nb = pre - b0 < SGL_VIS_BATCH ? (int) (pre - b0) : SGL_VIS_BATCH;
+        __syncthreads();
+        {
+          const int r = tid >> 2, q = tid & 3;
+          if (r < nb) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(P.prims + __ldg(list + b0 + r));
+            reinterpret_cast<uint4 *>(&sPrims[r].p)[q] = __ldg(src + q);
+          }
+          if (tid < nb) sSlots[tid] = __ldg(list + b0 + tid);
+        }
+        __syncthreads();
+        if (tid < nb && (sPrims[tid].p.flags & SGL_PF_KIND_MASK) == SGL_PK_TRIANGLE) sPrims[tid].e = sglTriEdge(sPrims[tid].p);
+        __syncthreads();
+        uint32_t rel[2];
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          const int i = hh * 32 + lane;
+          bool r = false;
+          if (i < nb) {
+            const SglVisPrim &vp = sPrims[i];
+            r = vp.p.bx0 <= wbx + 3 && vp.p.bx1 >= wbx && vp.p.by0 <= wby + 1 && vp.p.by1 >= wby;
+            if (r) {
+              const uint32_t kind = vp.p.flags & SGL_PF_KIND_MASK;
+              if (kind == SGL_PK_TRIANGLE) r = !sglTriSurelyOutside(vp.e, (float) wbx + 2.f, (float) wby + 1.f, 1.875f, 0.875f);
+              else if (kind == SGL_PK_LINE) r = sglLineNearRect(vp.p, wbx, wby, wbx + 3, wby + 1);
+            }
+          }
+          rel[hh] = __ballot_sync(0xffffffffu, r);
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          uint32_t m = rel[hh];
+          while (m) {
+            const int k = hh * 32 + __ffs(m) - 1;
+            m &= m - 1;
+            sglVisSamplePrim(P, sPrims[k], sSlots[k], px, py, smp, lane, inFb, depth, owner, hasColor, hasDepth);
+          }
+        }
+      }
+      if (inFb) {
+        if (hasDepth) P.depthBase[idx] = depth;
+        if (hasColor) P.vis[idx] = owner;
+      }
+      if (P.tileTimes) {
+        __syncthreads();
+        if (tid == 0 && quarter == 0) {
+          unsigned long long t;
+          asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+          P.tileTimes[2 * tile + 1] = t;
+        }
+      }
+      return;
+    }
+  }
   // a warp owns an 8x4 pixel block of the tile (same mapping as the shading kernel): small triangles then concern one
   // or two warps of the CTA instead of most 16x2 strips
   const int wbx = tx * SGL_TILE + (warp & 1) * 8, wby = ty * SGL_TILE + (warp >> 1) * 4;
@@ -362,6 +511,14 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS, SGL_VIS_MIN_BLOCKS) sglVisKe
       if (NS == 4) reinterpret_cast<uint4 *>(P.vis)[pix] =
           make_uint4(owner[0], owner[NS > 1 ? 1 : 0], owner[NS > 2 ? 2 : 0], owner[NS > 3 ? 3 : 0]);
       else P.vis[pix] = owner[0];
+    }
+  }
+  if (P.tileTimes) {
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      P.tileTimes[2 * tile + 1] = t;
     }
   }
 }

@@ -78,8 +78,14 @@ struct Ctx {
   };
   Arena arenas[3];
   int arenaNext = 0;
+  unsigned long long *dTileTimes = nullptr;        // sgl_debug_tile_times
+  size_t tileTimesCap = 0;
+  int tileTiming = 0;
+  const uint32_t *lastTileSortedCount = nullptr;   // of the most recent non-depth-only pass (instrumentation)
+  int lastTilesX = 0, lastTilesY = 0;
   cudaStream_t geomStream = nullptr;
   int noOverlap = 0;           // SGL_NO_OVERLAP=1: geometry and pixel stages on one stream (A/B runs)
+  int noSplit = 0;             // SGL_NO_SPLIT=1: heavy MSAA tiles are not split into quarter-tile CTAs (A/B runs)
   void *dummyTexels = nullptr; // backing store of texture table entry 0
   uint32_t *vis = nullptr;     // visibility buffer of the deferred path
   size_t visCap = 0;
@@ -308,7 +314,11 @@ int sgl_init(int device_ordinal, int rank, int world) {
   CU(cudaMemset(g.dCounters, 0, 8 * sizeof(unsigned long long)));
   CU(cudaEventCreate(&g.evBegin));
   CU(cudaEventCreate(&g.evEnd));
-  CU(cudaStreamCreateWithFlags(&g.geomStream, cudaStreamNonBlocking));
+  {  // geometry kernels are small and feed the pixel stage of the NEXT pass: give them priority over resident pixel work
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(cudaStreamCreateWithPriority(&g.geomStream, cudaStreamNonBlocking, hi));
+  }
   CU(cudaStreamCreateWithFlags(&g.copyStream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&g.copyReady, cudaEventDisableTiming));
   {  // texture table entry 0 = 1x1 RGBA8 dummy: what unbound maps read in the straight-line shader paths
@@ -329,6 +339,8 @@ int sgl_init(int device_ordinal, int rank, int world) {
     g.forceFused = (ff && atoi(ff) != 0) ? 1 : 0;
     const char *no = getenv("SGL_NO_OVERLAP");
     g.noOverlap = (no && atoi(no) != 0) ? 1 : 0;
+    const char *ns = getenv("SGL_NO_SPLIT");
+    g.noSplit = (ns && atoi(ns) != 0) ? 1 : 0;
   }
   g.ready = true;
   g.err.clear();
@@ -360,6 +372,7 @@ int sgl_shutdown(void) {
   if (g.dummyTexels) cudaFree(g.dummyTexels);
   if (g.dTileOwner) cudaFree(g.dTileOwner);
   if (g.dOwnerPrefix) cudaFree(g.dOwnerPrefix);
+  if (g.dTileTimes) cudaFree(g.dTileTimes);
   for (void *m : g.peerMaps) cudaIpcCloseMemHandle(m);
   for (void *a : g.peerAllocs) cudaFree(a);
   if (g.dCounters) cudaFree(g.dCounters);
@@ -446,9 +459,15 @@ int sgl_get_kernel_times(SglKernelTime *out, int capacity) {
   cudaStreamSynchronize(g.stream);
   if (g.geomStream) cudaStreamSynchronize(g.geomStream);
   int n = 0;
+  const bool dump = getenv("SGL_PROFILE_OVERLAP") != nullptr && !gProf.empty();
   for (auto &p : gProf) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, p.a, p.b);
+    if (dump) {   // timeline relative to the first recorded launch
+      float t0 = 0.f;
+      cudaEventElapsedTime(&t0, gProf.front().a, p.a);
+      fprintf(stderr, "[sgl timeline] %-22s start %9.1f us  dur %7.1f us\n", p.name, t0 * 1e3f, ms * 1e3f);
+    }
     int k = 0;
     for (; k < n; k++)
       if (!strcmp(out[k].name, p.name)) break;
@@ -890,7 +909,8 @@ int sgl_pass_end(void) {
   uint8_t *A = arena.mem;
   // geometry stages go to their own stream unless overlap is off or per-kernel profiling wants clean timings;
   // the arena slot is recycled only after the pixel stages of the pass that used it last have finished
-  const bool overlap = !g.noOverlap && !gProfiling;
+  static const bool profileOverlapped = getenv("SGL_PROFILE_OVERLAP") != nullptr;   // timeline dumps (development)
+  const bool overlap = !g.noOverlap && (!gProfiling || profileOverlapped);
   struct StageGuard { ~StageGuard() { gCur = nullptr; } } stageGuard;
   gCur = overlap ? g.geomStream : g.stream;
   if (arena.used && overlap) CU(cudaStreamWaitEvent(g.geomStream, arena.pixelDone, 0));
@@ -964,13 +984,16 @@ int sgl_pass_end(void) {
   P.binCapacity = (uint32_t) binCapacity;
   P.tileSorted = depthOnly ? nullptr : (uint32_t *) (A + oTileSorted);
   P.tileSortedCount = depthOnly ? nullptr : (uint32_t *) (A + oTileSortedCount);
+  if (!depthOnly) { g.lastTileSortedCount = (const uint32_t *) (A + oTileSortedCount); g.lastTilesX = tilesX; g.lastTilesY = tilesY; }
   P.tileOrder = depthOnly ? nullptr : (uint32_t *) (A + oTileOrder);
   P.tileClassCount = (uint32_t *) (A + oTileClassCount);
+  P.splitCap = (!depthOnly && samples == 4 && !g.noSplit) ? std::max(nTiles / 4, 1) : 0;
   P.bigList = (uint32_t *) (A + oBigList);
   P.bigCount = (uint32_t *) (A + oBigCount);
   P.bigCapacity = (uint32_t) std::max(primSlots, 1);
   P.textures = g.dTextures;
   P.counters = g.dCounters;
+  if (g.tileTiming && ct && (size_t) nTiles * 2 <= g.tileTimesCap) P.tileTimes = g.dTileTimes;
 
   if (depthOnly) {
     if (maxVerts > 0) {
@@ -1028,14 +1051,17 @@ int sgl_pass_end(void) {
       if (rc) return rc;
     }
   }
-  rc = launch("sglTileScanKernel", sglTileScanKernel, dim3(1), dim3(1024), (const uint32_t *) P.tileCount, P.tileOffset, nTiles, g.dCounters);
+  rc = launch("sglTileScanKernel", sglTileScanKernel, dim3(1), dim3(1024), (const uint32_t *) P.tileCount, P.tileOffset, nTiles, g.dCounters,
+              P.tileOrder, P.tileClassCount, P.tileSortedCount, P.tileOwner, g.rank);
   if (rc) return rc;
   if (nDraws && maxSlots > 0) {
     rc = launch("sglBinFillKernel", sglBinFillKernel, dim3((maxSlots + 255) / 256, nDraws), dim3(256), P);
     if (rc) return rc;
   }
-  rc = launch("sglTileSortKernel", sglTileSortKernel, dim3(nTiles), dim3(128), P);
-  if (rc) return rc;
+  if (P.splitCap > 0) {   // lists of the tiles the MSAA visibility kernel splits
+    rc = launch("sglTileSortKernel", sglTileSortKernel, dim3((P.splitCap + SGL_TILE_SORT_WARPS - 1) / SGL_TILE_SORT_WARPS), dim3(32 * SGL_TILE_SORT_WARPS), P);
+    if (rc) return rc;
+  }
   rc = toPixelStage();
   if (rc) return rc;
   // Deferred (visibility + shading) path for passes made of opaque draws whose point/line programs have no varyings;
@@ -1089,6 +1115,32 @@ int sgl_pass_end(void) {
     if (e != 0) return fail(SGL_ERR_CUDA, "raster kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
   }
   return passDone();
+}
+
+// instrumentation: per-tile primitive list lengths of the most recent colour pass (SGL_TILE_UNSORTED = overflow tile)
+int sgl_get_tile_list_sizes(uint32_t *out, int capacity, int *tiles_x_out, int *tiles_y_out) {
+  NEED_CTX();
+  if (!g.lastTileSortedCount) return fail(SGL_ERR_STATE, "no pass recorded yet");
+  { int rc = syncAll(); if (rc) return rc; }
+  int n = g.lastTilesX * g.lastTilesY;
+  if (tiles_x_out) *tiles_x_out = g.lastTilesX;
+  if (tiles_y_out) *tiles_y_out = g.lastTilesY;
+  if (out) CU(cudaMemcpy(out, g.lastTileSortedCount, sizeof(uint32_t) * std::min(n, capacity), cudaMemcpyDeviceToHost));
+  return SGL_OK;
+}
+
+// instrumentation: per-tile start/end time (globaltimer ns) of the visibility kernel of the most recent colour pass
+int sgl_debug_tile_times(int enable, unsigned long long *out, int capacity_tiles) {
+  NEED_CTX();
+  { int rc = syncAll(); if (rc) return rc; }
+  if (out && g.dTileTimes) CU(cudaMemcpy(out, g.dTileTimes, sizeof(unsigned long long) * 2 * std::min<size_t>(capacity_tiles, g.tileTimesCap / 2), cudaMemcpyDeviceToHost));
+  g.tileTiming = enable;
+  if (enable && !g.dTileTimes) {
+    g.tileTimesCap = 2 * 1024 * 1024;
+    CU(cudaMalloc(&g.dTileTimes, g.tileTimesCap * sizeof(unsigned long long)));
+    CU(cudaMemset(g.dTileTimes, 0, g.tileTimesCap * sizeof(unsigned long long)));
+  }
+  return SGL_OK;
 }
 
 // ---- multi-GPU --------------------------------------------------------------------------------------------------
