@@ -33,25 +33,63 @@ def _env_rank():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe): NVML polled every 5 ms when
+    pynvml is importable (a 70 ms timed region still gets ~10 samples), else `nvidia-smi` every 200 ms."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
-        self.rows = []
+        self.rows = []          # (sm_mhz, sm_max_mhz, set of reasons)
         self.stop = threading.Event()
         self.idx = gpu_index
         self.t = threading.Thread(target=self._run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(gpu_index))
+        except Exception:
+            self.nvml = None
 
-    def _run(self):
+    @staticmethod
+    def _physical_index(i):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[i])
+            except Exception:
+                return i
+        return i
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = get(self.h)
+        masks = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        self.rows.append((sm, mx, {k for k, m in masks.items() if bits & m}))
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        r = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5)
+        c = [x.strip() for x in r.stdout.strip().split(",")]
+        if len(c) >= 7 and c[0].replace(".", "").isdigit():
+            self.rows.append((int(float(c[0])), int(float(c[1])), {self.NAMES[i] for i in range(4) if c[3 + i].lower().startswith("active")}))
+
+    def _run(self):
         while not self.stop.is_set():
             try:
-                r = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5)
-                self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+                if self.nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.005 if self.nvml else 0.2)
 
     def __enter__(self):
         self.t.start()
@@ -62,12 +100,11 @@ class ClockSampler:
         self.t.join(timeout=5)
 
     def summary(self):
-        sm = sorted(int(float(r[0])) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
-        mx = [int(float(r[1])) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        sm = sorted(r[0] for r in self.rows)
+        mx = [r[1] for r in self.rows]
+        reasons = sorted(set().union(*[r[2] for r in self.rows])) if self.rows else []
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def cpu_reference_fps(trace, data_dir, frames, warmup):
@@ -238,6 +275,7 @@ def main():
         sync_all()
         elapsed_ms = _max_over_ranks(ms.value, world)
     ctr = capi.counters()
+    clocks_summary = clocks.summary()
 
     # ---- timed region 2: end to end through the public API with host buffers: per frame the draw records / uniform
     #      snapshots are uploaded from pinned memory and the finished frame is read back into pinned host memory
@@ -275,7 +313,7 @@ def main():
             "gfrag_per_s": fps * frags_per_frame / 1e9, "fragments_per_frame": frags_per_frame,
             "e2e": {"value": frames_per_step * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d // K,
                     "d2h_bytes_per_step": d2h // K},
-            "gpu_launches": launches, "clocks": clocks.summary(), "host_submit_ms_per_step": host_submit_ms}
+            "gpu_launches": launches, "clocks": clocks_summary, "host_submit_ms_per_step": host_submit_ms}
     if rank == 0:
         line["roofline"] = roofline_block(ktimes, ctr, K, data)
         line["kernel_ms_per_frame"] = {k: v[1] / 20.0 for k, v in sorted(ktimes.items())}

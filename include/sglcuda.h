@@ -100,6 +100,8 @@ typedef struct SglCounters {
   uint64_t clip_overflow;     /* primitives dropped because the clip-vertex arena was full (should be 0) */
   uint64_t h2d_bytes;         /* host->device bytes copied by passes (draw records incl. uniform snapshots) and uploads */
   uint64_t d2h_bytes;         /* device->host bytes copied by read-backs */
+  uint64_t host_ns_pass_end;  /* CPU time spent inside sgl_pass_end (arena layout, uploads, launches) */
+  uint64_t host_ns_draw;      /* CPU time spent inside sgl_draw (state snapshot) */
 } SglCounters;
 
 /* ---- context ---------------------------------------------------------------------------------------- */

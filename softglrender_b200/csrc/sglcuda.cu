@@ -7,6 +7,7 @@
 #include "sgl_kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -101,7 +102,7 @@ struct Ctx {
   std::vector<void *> peerAllocs, peerMaps;
   // counters
   unsigned long long *dCounters = nullptr;
-  unsigned long long hostLaunches = 0, hostPasses = 0, hostDraws = 0, hostH2D = 0, hostD2H = 0;
+  unsigned long long hostLaunches = 0, hostPasses = 0, hostDraws = 0, hostH2D = 0, hostD2H = 0, hostNsPassEnd = 0, hostNsDraw = 0;
   cudaEvent_t evBegin = nullptr, evEnd = nullptr;
   std::string err;
 };
@@ -423,6 +424,8 @@ int sgl_get_counters(SglCounters *out) {
   out->clip_overflow = c[7];
   out->h2d_bytes = g.hostH2D;
   out->d2h_bytes = g.hostD2H;
+  out->host_ns_pass_end = g.hostNsPassEnd;
+  out->host_ns_draw = g.hostNsDraw;
   return SGL_OK;
 }
 
@@ -430,7 +433,7 @@ int sgl_reset_counters(void) {
   NEED_CTX();
   { int rc = syncAll(); if (rc) return rc; }
   CU(cudaMemset(g.dCounters, 0, 8 * sizeof(unsigned long long)));
-  g.hostLaunches = g.hostPasses = g.hostDraws = g.hostH2D = g.hostD2H = 0;
+  g.hostLaunches = g.hostPasses = g.hostDraws = g.hostH2D = g.hostD2H = g.hostNsPassEnd = g.hostNsDraw = 0;
   return SGL_OK;
 }
 
@@ -774,8 +777,18 @@ int sgl_set_viewport(int x, int y, int width, int height) {
   return SGL_OK;
 }
 
+namespace {
+struct HostTimer {
+  unsigned long long &acc;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit HostTimer(unsigned long long &a) : acc(a) {}
+  ~HostTimer() { acc += (unsigned long long) std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); }
+};
+}  // namespace
+
 int sgl_draw(const SglDraw *draw) {
   NEED_CTX();
+  HostTimer hostTimer(g.hostNsDraw);
   if (!g.inPass) return fail(SGL_ERR_STATE, "sgl_draw outside a render pass");
   if (!draw || !shaderMeta(draw->shader)) return fail(SGL_ERR_INVALID, "unknown shader %d", draw ? draw->shader : -1);
   if (draw->vertex_buffer <= 0 || draw->vertex_buffer >= (int) g.buffers.size() || !g.buffers[draw->vertex_buffer].d)
@@ -822,6 +835,7 @@ int sgl_draw(const SglDraw *draw) {
 
 int sgl_pass_end(void) {
   NEED_CTX();
+  HostTimer hostTimer(g.hostNsPassEnd);
   if (!g.inPass) return fail(SGL_ERR_STATE, "sgl_pass_end outside a pass");
   g.inPass = false;
   TextureRec *ct = g.colorTex ? tex(g.colorTex) : nullptr;

@@ -67,7 +67,8 @@ def main():
         r = {"workload": name, "units_per_s": units * steps / (ms.value / 1e3), "unit": "views/s" if key == "c5" else "frames/s",
              "ms_per_step": ms.value / steps, "host_submit_ms_per_step": host_ms, "fragments_per_step": ctr["fragments_shaded"] / steps,
              "gfrag_per_s": ctr["fragments_shaded"] / (ms.value / 1e3) / 1e9, "primitives_per_step": ctr["primitives_in"] / steps,
-             "clip_overflow": ctr["clip_overflow"], "kernel_ms_per_step": {k: v[1] / 3.0 for k, v in sorted(kt.items())}}
+             "clip_overflow": ctr["clip_overflow"], "host_us_pass_end_per_step": ctr["host_ns_pass_end"] / 1e3 / steps,
+             "host_us_draw_per_step": ctr["host_ns_draw"] / 1e3 / steps, "passes_per_step": ctr["passes"] / steps, "draws_per_step": ctr["draws"] / steps, "kernel_ms_per_step": {k: v[1] / 3.0 for k, v in sorted(kt.items())}}
         if args.cpu and os.path.exists(workloads.REF_PLAYER) and key != "c4big":
             c = workloads.run_player(workloads.REF_PLAYER, trace, data_dir=data, frames=5 if key != "c5" else 2, warmup=1)
             r["cpu_reference"] = {"units_per_s": units * 1000.0 / c["ms_median"], "ms_per_step": c["ms_median"], "cores": os.cpu_count()}
