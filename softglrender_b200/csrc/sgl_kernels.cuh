@@ -234,7 +234,11 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS) sglRasterKernel(SglPassParam
   SglPixelState<NS> st;
 #pragma unroll
   for (int s = 0; s < NS; s++) { st.depth[s] = P.clearDepth; st.color[s] = P.clearColor; st.owner[s] = SGL_OWNER_NONE; }
-  if (inFb) {
+  bool loaded = false;
+  auto loadState = [&]() {   // attachments that are not cleared are read once, after the first gather (empty tiles may skip it)
+    if (loaded) return;
+    loaded = true;
+    if (!inFb) return;
     if (hasDepth && !P.clearDepthFlag) {
       if (NS == 4) {
         float4 dq = reinterpret_cast<const float4 *>(P.depthBase)[pix];
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS) sglRasterKernel(SglPassParam
         st.color[0] = cq.x; st.color[NS > 1 ? 1 : 0] = cq.y; st.color[NS > 2 ? 2 : 0] = cq.z; st.color[NS > 3 ? 3 : 0] = cq.w;
       } else st.color[0] = reinterpret_cast<const uint32_t *>(P.colorBase)[pix];
     }
-  }
+  };
 
   const uint32_t off = P.tileOffset[tile];
   uint32_t nList = P.tileOffset[tile + 1] - off;
@@ -292,6 +296,8 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS) sglRasterKernel(SglPassParam
       __syncthreads();
     }
     const int n = sCount;
+    if (P.skipEmptyTiles && !loaded && n == 0 && hi == keyEnd) return;   // nothing touches this tile: it keeps its content
+    loadState();
     if (n > 1) {
       int n2 = 1;
       while (n2 < n) n2 <<= 1;

@@ -106,6 +106,7 @@ struct SglPassParams {
   uint32_t *vis;            // visibility buffer of the deferred path: owner (slot | shading sample << 29) [y][x][sample]
   int32_t fbW, fbH, samples;
   int32_t clearColorFlag, clearDepthFlag;
+  int32_t skipEmptyTiles;   // fused kernel, tail of a split pass (both clear flags off): tiles without primitives keep their content
   uint32_t clearColor;      // RGBA8 packed (RendererSoft.cpp:72-75)
   float clearDepth;
   // tiles

@@ -86,6 +86,7 @@ struct Ctx {
   int lastTilesX = 0, lastTilesY = 0;
   cudaStream_t geomStream = nullptr;
   int noOverlap = 0;           // SGL_NO_OVERLAP=1: geometry and pixel stages on one stream (A/B runs)
+  int noPassSplit = 0;         // SGL_NO_PASS_SPLIT=1: a pass with a blended tail runs entirely in the fused kernel (A/B runs)
   int noSplit = 0;             // SGL_NO_SPLIT=1: heavy MSAA tiles are not split into quarter-tile CTAs (A/B runs)
   void *dummyTexels = nullptr; // backing store of texture table entry 0
   uint32_t *vis = nullptr;     // visibility buffer of the deferred path
@@ -340,6 +341,8 @@ int sgl_init(int device_ordinal, int rank, int world) {
     g.forceFused = (ff && atoi(ff) != 0) ? 1 : 0;
     const char *no = getenv("SGL_NO_OVERLAP");
     g.noOverlap = (no && atoi(no) != 0) ? 1 : 0;
+    const char *nps = getenv("SGL_NO_PASS_SPLIT");
+    g.noPassSplit = (nps && atoi(nps) != 0) ? 1 : 0;
     const char *ns = getenv("SGL_NO_SPLIT");
     g.noSplit = (ns && atoi(ns) != 0) ? 1 : 0;
   }
@@ -833,27 +836,26 @@ int sgl_draw(const SglDraw *draw) {
   return SGL_OK;
 }
 
-int sgl_pass_end(void) {
-  NEED_CTX();
-  HostTimer hostTimer(g.hostNsPassEnd);
-  if (!g.inPass) return fail(SGL_ERR_STATE, "sgl_pass_end outside a pass");
-  g.inPass = false;
+namespace {
+// One (sub-)pass over `draws` into the current attachments.  A render pass is normally one call; a pass whose tail
+// needs the ordered fused kernel (blending, lines/points of programs with varyings) is run as two: the opaque head takes
+// the deferred visibility + shading path, the tail loads what the head wrote (clear flags off).
+int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFlag, bool tailOfSplit) {
   TextureRec *ct = g.colorTex ? tex(g.colorTex) : nullptr;
   TextureRec *dt = g.depthTex ? tex(g.depthTex) : nullptr;
-  if ((g.colorTex && !ct) || (g.depthTex && !dt)) return fail(SGL_ERR_INVALID, "attachment destroyed during pass");
   const int fbW = ct ? sglLevelDim(ct->obj.width, g.colorLevel) : dt->obj.width;
   const int fbH = ct ? sglLevelDim(ct->obj.height, g.colorLevel) : dt->obj.height;
   const int samples = ct ? ct->obj.samples : dt->obj.samples;
   const int tilesX = (fbW + SGL_TILE - 1) / SGL_TILE, tilesY = (fbH + SGL_TILE - 1) / SGL_TILE;
   const int nTiles = tilesX * tilesY;
-  const int nDraws = (int) g.draws.size();
+  const int nDraws = (int) draws.size();
 
   // Depth-only passes whose result is order independent (filled triangles, depth test + write on, one direction of
   // depth function) skip binning entirely: prim-parallel setup with atomicMin/Max rasterisation (sgl_depth.cuh).
   bool depthOnly = !g.forceFused && !ct && dt && nDraws > 0;
   int dir = 0;
   for (int i = 0; i < nDraws && depthOnly; i++) {
-    const SglRenderStates &rs = g.draws[i].rs;
+    const SglRenderStates &rs = draws[i].rs;
     int f = rs.depth_func;
     int d = (f == 1 || f == 3) ? 1 : ((f == 4 || f == 6) ? 2 : 0);
     if (rs.primitive_type != SGL_PRIM_TRIANGLE || rs.polygon_mode != SGL_POLY_FILL || !rs.depth_test || !rs.depth_mask || d == 0 ||
@@ -877,7 +879,7 @@ int sgl_pass_end(void) {
   int primSlots = 0, keyBase = 0, maxVerts = 0, maxPrims = 0, maxSlots = 0;
   std::vector<size_t> oClip(nDraws), oFrag(nDraws), oMask(nDraws), oVout(nDraws), oVary(nDraws);
   for (int i = 0; i < nDraws; i++) {
-    SglDrawRec &r = g.draws[i];
+    SglDrawRec &r = draws[i];
     const int pt = r.rs.primitive_type;
     const int per = pt == SGL_PRIM_TRIANGLE ? 3 : (pt == SGL_PRIM_LINE ? 2 : 1);
     r.inputPrims = r.indexCount / per;
@@ -939,14 +941,12 @@ int sgl_pass_end(void) {
   auto passDone = [&]() -> int {
     CU(cudaEventRecord(arena.pixelDone, g.stream));
     arena.used = true;
-    g.hostPasses++;
     g.hostDraws += nDraws;
-    g.draws.clear();
     return SGL_OK;
   };
 
   for (int i = 0; i < nDraws; i++) {
-    SglDrawRec &r = g.draws[i];
+    SglDrawRec &r = draws[i];
     r.clipPos = (float *) (A + oClip[i]);
     r.fragPos = (float *) (A + oFrag[i]);
     r.clipMask = (int32_t *) (A + oMask[i]);
@@ -960,7 +960,7 @@ int sgl_pass_end(void) {
     Staging *st = nullptr;
     rc = stagingAcquire(sizeof(SglDrawRec) * nDraws, &st);
     if (rc) return rc;
-    memcpy(st->host, g.draws.data(), sizeof(SglDrawRec) * nDraws);
+    memcpy(st->host, draws.data(), sizeof(SglDrawRec) * nDraws);
     CU(cudaMemcpyAsync(A + oDraws, st->host, sizeof(SglDrawRec) * nDraws, cudaMemcpyHostToDevice, gCur));
     g.hostH2D += sizeof(SglDrawRec) * nDraws;
     CU(cudaEventRecord(st->done, gCur));
@@ -974,8 +974,9 @@ int sgl_pass_end(void) {
   P.resolveBase = (ct && samples > 1) ? ct->obj.resolve : nullptr;
   P.mirrorBase = (ct && g.colorLayer == 0 && g.colorLevel == 0) ? (uint8_t *) ct->mirror : nullptr;
   P.fbW = fbW; P.fbH = fbH; P.samples = samples;
-  P.clearColorFlag = g.clearColorFlag;
-  P.clearDepthFlag = g.clearDepthFlag;
+  P.clearColorFlag = clearColorFlag;
+  P.clearDepthFlag = clearDepthFlag;
+  P.skipEmptyTiles = (tailOfSplit && !clearColorFlag && !clearDepthFlag) ? 1 : 0;
   {  // RGBA(clear * 255) truncation (RendererSoft.cpp:72-75)
     uint32_t c = 0;
     for (int k = 0; k < 4; k++) c |= ((uint32_t) (uint8_t) (int) (g.clearColor[k] * 255.f)) << (8 * k);
@@ -1016,7 +1017,7 @@ int sgl_pass_end(void) {
     }
     rc = toPixelStage();   // the atomic rasteriser writes the depth attachment
     if (rc) return rc;
-    if (g.clearDepthFlag) {
+    if (clearDepthFlag) {
       uint32_t bits;
       memcpy(&bits, &g.clearDepth, 4);
       size_t n = (size_t) fbW * fbH * samples;
@@ -1082,7 +1083,7 @@ int sgl_pass_end(void) {
   // everything else (blending, wireframe with a lit program) takes the fused tile kernel.
   bool deferred = !g.forceFused;
   for (int i = 0; i < nDraws && deferred; i++) {
-    const SglDrawRec &r = g.draws[i];
+    const SglDrawRec &r = draws[i];
     const bool fill = r.rs.primitive_type == SGL_PRIM_TRIANGLE && r.rs.polygon_mode == SGL_POLY_FILL;
     if (r.rs.blend && ct) deferred = false;
     if (!fill && r.varyingCount != 0) deferred = false;
@@ -1129,6 +1130,41 @@ int sgl_pass_end(void) {
     if (e != 0) return fail(SGL_ERR_CUDA, "raster kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
   }
   return passDone();
+}
+
+// can this draw take the deferred (visibility + shading) path?  Blending is order dependent; point/line fragments of
+// programs with varyings carry per-step varyings that the visibility buffer cannot reproduce.
+bool drawIsDeferrable(const SglDrawRec &r, bool hasColor) {
+  const bool fill = r.rs.primitive_type == SGL_PRIM_TRIANGLE && r.rs.polygon_mode == SGL_POLY_FILL;
+  if (r.rs.blend && hasColor) return false;
+  if (!fill && r.varyingCount != 0) return false;
+  return true;
+}
+}  // namespace
+
+int sgl_pass_end(void) {
+  NEED_CTX();
+  HostTimer hostTimer(g.hostNsPassEnd);
+  if (!g.inPass) return fail(SGL_ERR_STATE, "sgl_pass_end outside a pass");
+  g.inPass = false;
+  TextureRec *ct = g.colorTex ? tex(g.colorTex) : nullptr;
+  TextureRec *dt = g.depthTex ? tex(g.depthTex) : nullptr;
+  if ((g.colorTex && !ct) || (g.depthTex && !dt)) return fail(SGL_ERR_INVALID, "attachment destroyed during pass");
+  const int nDraws = (int) g.draws.size();
+  int rc;
+  // split point: the first draw that cannot be deferred, when a deferrable head of real size precedes it
+  int k = 0;
+  while (k < nDraws && drawIsDeferrable(g.draws[k], ct != nullptr)) k++;
+  if (ct && !g.forceFused && !g.noPassSplit && k > 0 && k < nDraws) {
+    std::vector<SglDrawRec> head(g.draws.begin(), g.draws.begin() + k), tail(g.draws.begin() + k, g.draws.end());
+    rc = runPass(head, g.clearColorFlag, g.clearDepthFlag, false);
+    if (rc == SGL_OK) rc = runPass(tail, 0, 0, true);
+  } else {
+    rc = runPass(g.draws, g.clearColorFlag, g.clearDepthFlag, false);
+  }
+  g.hostPasses++;
+  g.draws.clear();
+  return rc;
 }
 
 // instrumentation: per-tile primitive list lengths of the most recent colour pass (SGL_TILE_UNSORTED = overflow tile)
