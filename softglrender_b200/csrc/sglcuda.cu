@@ -85,6 +85,13 @@ struct Ctx {
   const uint32_t *lastTileSortedCount = nullptr;   // of the most recent non-depth-only pass (instrumentation)
   int lastTilesX = 0, lastTilesY = 0;
   cudaStream_t geomStream = nullptr;
+  // depth-only passes (shadow maps) run their pixel stage on an auxiliary stream: they start when all earlier pixel work
+  // is done and only the next kernel that SAMPLES textures (or touches their depth texture) waits for them, so the
+  // shadow pass of a frame overlaps the visibility kernel of its main pass
+  cudaStream_t auxStream = nullptr;
+  cudaEvent_t auxReady = nullptr, auxDone = nullptr;
+  bool auxPending = false;
+  int auxDepthTex = 0;
   int noOverlap = 0;           // SGL_NO_OVERLAP=1: geometry and pixel stages on one stream (A/B runs)
   int noPassSplit = 0;         // SGL_NO_PASS_SPLIT=1: a pass with a blended tail runs entirely in the fused kernel (A/B runs)
   int noSplit = 0;             // SGL_NO_SPLIT=1: heavy MSAA tiles are not split into quarter-tile CTAs (A/B runs)
@@ -120,14 +127,27 @@ int fail(int code, const char *fmt, ...) {
   return code;
 }
 
+void joinAux();
+
 #define CU(call)                                                                                     \
   do {                                                                                               \
     cudaError_t e_ = (call);                                                                         \
     if (e_ != cudaSuccess) return fail(SGL_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
   } while (0)
 
-#define NEED_CTX() \
+// Entry points that only record host state (pass_begin / set_viewport / draw / pass_end) use NEED_CTX_RECORDING; every
+// other entry point first orders the main stream behind a depth-only pass still running on the auxiliary stream.
+#define NEED_CTX_RECORDING() \
   if (!g.ready) return fail(SGL_ERR_STATE, "sgl_init has not been called (or failed)")
+#define NEED_CTX()        \
+  NEED_CTX_RECORDING();   \
+  joinAux()
+
+void joinAux() {
+  if (!g.auxPending) return;
+  cudaStreamWaitEvent(g.stream, g.auxDone, 0);
+  g.auxPending = false;
+}
 
 size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -170,6 +190,8 @@ uint8_t *levelPtr(const TextureRec &t, int layer, int level) {
 int syncAll() {
   CU(cudaStreamSynchronize(g.stream));
   if (g.geomStream) CU(cudaStreamSynchronize(g.geomStream));
+  if (g.auxStream) CU(cudaStreamSynchronize(g.auxStream));
+  g.auxPending = false;
   return SGL_OK;
 }
 
@@ -321,6 +343,9 @@ int sgl_init(int device_ordinal, int rank, int world) {
     CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CU(cudaStreamCreateWithPriority(&g.geomStream, cudaStreamNonBlocking, hi));
   }
+  CU(cudaStreamCreateWithFlags(&g.auxStream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&g.auxReady, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&g.auxDone, cudaEventDisableTiming));
   CU(cudaStreamCreateWithFlags(&g.copyStream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&g.copyReady, cudaEventDisableTiming));
   {  // texture table entry 0 = 1x1 RGBA8 dummy: what unbound maps read in the straight-line shader paths
@@ -372,6 +397,9 @@ int sgl_shutdown(void) {
     if (a.pixelDone) cudaEventDestroy(a.pixelDone);
   }
   if (g.geomStream) cudaStreamDestroy(g.geomStream);
+  if (g.auxStream) { cudaStreamSynchronize(g.auxStream); cudaStreamDestroy(g.auxStream); }
+  if (g.auxReady) cudaEventDestroy(g.auxReady);
+  if (g.auxDone) cudaEventDestroy(g.auxDone);
   if (g.vis) cudaFree(g.vis);
   if (g.dummyTexels) cudaFree(g.dummyTexels);
   if (g.dTileOwner) cudaFree(g.dTileOwner);
@@ -737,7 +765,7 @@ int sgl_readback_wait(void) {
 // ---- render pass ----------------------------------------------------------------------------------------------
 int sgl_pass_begin(int color_tex, int color_layer, int color_level, int depth_tex, int clear_color_flag,
                    int clear_depth_flag, const float clear_color[4], float clear_depth) {
-  NEED_CTX();
+  NEED_CTX_RECORDING();
   if (g.inPass) return fail(SGL_ERR_STATE, "sgl_pass_begin inside a pass");
   if (color_tex && !tex(color_tex)) return fail(SGL_ERR_INVALID, "bad colour attachment %d", color_tex);
   if (depth_tex && !tex(depth_tex)) return fail(SGL_ERR_INVALID, "bad depth attachment %d", depth_tex);
@@ -772,7 +800,7 @@ int sgl_pass_begin(int color_tex, int color_layer, int color_level, int depth_te
 }
 
 int sgl_set_viewport(int x, int y, int width, int height) {
-  NEED_CTX();
+  NEED_CTX_RECORDING();
   g.vpX = (float) x;
   g.vpY = (float) y;
   g.vpW = (float) width;
@@ -790,7 +818,7 @@ struct HostTimer {
 }  // namespace
 
 int sgl_draw(const SglDraw *draw) {
-  NEED_CTX();
+  NEED_CTX_RECORDING();
   HostTimer hostTimer(g.hostNsDraw);
   if (!g.inPass) return fail(SGL_ERR_STATE, "sgl_draw outside a render pass");
   if (!draw || !shaderMeta(draw->shader)) return fail(SGL_ERR_INVALID, "unknown shader %d", draw ? draw->shader : -1);
@@ -1015,8 +1043,19 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
       rc = launch("sglVertexKernel", sglVertexKernel, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws);
       if (rc) return rc;
     }
-    rc = toPixelStage();   // the atomic rasteriser writes the depth attachment
-    if (rc) return rc;
+    // pixel stage (the atomic rasteriser writes the depth attachment): on the auxiliary stream when overlap is on
+    const bool aux = overlap;
+    cudaStream_t pix = aux ? g.auxStream : g.stream;
+    if (aux) {
+      CU(cudaEventRecord(g.auxReady, g.stream));           // all earlier pixel work (it may sample this depth texture) first
+      CU(cudaStreamWaitEvent(g.auxStream, g.auxReady, 0));
+      CU(cudaEventRecord(arena.geomDone, g.geomStream));
+      CU(cudaStreamWaitEvent(g.auxStream, arena.geomDone, 0));
+      gCur = g.auxStream;
+    } else {
+      rc = toPixelStage();
+      if (rc) return rc;
+    }
     if (clearDepthFlag) {
       uint32_t bits;
       memcpy(&bits, &g.clearDepth, 4);
@@ -1043,10 +1082,19 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     D.rank = g.rank;
     if (maxPrims > 0) {
       profBegin(samples == 4 ? "sglDepthOnly<4>" : "sglDepthOnly<1>");
-      int e = sglLaunchDepthOnly(samples, &D, maxPrims, nDraws, nTiles, (void *) g.stream);
+      int e = sglLaunchDepthOnly(samples, &D, maxPrims, nDraws, nTiles, (void *) pix);
       profEnd();
       g.hostLaunches += 3;
       if (e != 0) return fail(SGL_ERR_CUDA, "depth-only kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
+    }
+    if (aux) {
+      CU(cudaEventRecord(g.auxDone, g.auxStream));
+      CU(cudaEventRecord(arena.pixelDone, g.auxStream));
+      g.auxPending = true;
+      g.auxDepthTex = g.depthTex;
+      arena.used = true;
+      g.hostDraws += nDraws;
+      return SGL_OK;
     }
     return passDone();
   }
@@ -1079,6 +1127,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   }
   rc = toPixelStage();
   if (rc) return rc;
+  if (g.auxPending && (g.depthTex == g.auxDepthTex || !overlap)) joinAux();   // this pass writes that depth texture
   // Deferred (visibility + shading) path for passes made of opaque draws whose point/line programs have no varyings;
   // everything else (blending, wireframe with a lit program) takes the fused tile kernel.
   bool deferred = !g.forceFused;
@@ -1107,6 +1156,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     profEnd();
     g.hostLaunches++;
     if (e != 0) return fail(SGL_ERR_CUDA, "visibility kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
+    joinAux();   // the shading kernel samples textures (shadow maps): depth-only passes on the auxiliary stream first
     if (ct) {
       if (ct->rbPending) {   // an asynchronous read-back of this image is still in flight: overwrite only after it
         CU(cudaStreamWaitEvent(g.stream, ct->rbDone, 0));
@@ -1119,6 +1169,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
       if (e != 0) return fail(SGL_ERR_CUDA, "shading kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
     }
   } else {
+    joinAux();
     if (ct && ct->rbPending) {
       CU(cudaStreamWaitEvent(g.stream, ct->rbDone, 0));
       ct->rbPending = false;
@@ -1143,7 +1194,7 @@ bool drawIsDeferrable(const SglDrawRec &r, bool hasColor) {
 }  // namespace
 
 int sgl_pass_end(void) {
-  NEED_CTX();
+  NEED_CTX_RECORDING();
   HostTimer hostTimer(g.hostNsPassEnd);
   if (!g.inPass) return fail(SGL_ERR_STATE, "sgl_pass_end outside a pass");
   g.inPass = false;
