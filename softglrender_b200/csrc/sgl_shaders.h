@@ -439,7 +439,8 @@ SGL_HD V4 sglFsPbrFast(const SglFsCtx &c, const float *v) {
 SGL_HD bool sglSamplerIsSimple(int shader, int slot, const SglTexObj &t, int filter, int wrap) {
   if (t.base == nullptr || t.format != SGL_FMT_RGBA8 || t.samples != 1 || t.layout != SGL_LAYOUT_LINEAR) return false;
   if (wrap != SGL_WRAP_REPEAT && wrap != SGL_WRAP_CLAMP_TO_EDGE) return false;
-  const bool cubeSlot = shader == SGL_SHADER_PBR && (slot == SGL_SLOT_PBR_IRRADIANCE || slot == SGL_SLOT_PBR_PREFILTER);
+  const bool cubeSlot = (shader == SGL_SHADER_PBR && (slot == SGL_SLOT_PBR_IRRADIANCE || slot == SGL_SLOT_PBR_PREFILTER)) ||
+                        (shader == SGL_SHADER_SKYBOX && slot == SGL_SLOT_SKY_CUBE);
   if (t.layers != (cubeSlot ? 6 : 1)) return false;
   if (filter == SGL_FILTER_LINEAR) return true;
   return shader == SGL_SHADER_PBR && slot == SGL_SLOT_PBR_PREFILTER && filter == SGL_FILTER_LINEAR_MIPMAP_LINEAR;
@@ -461,6 +462,14 @@ SGL_HD V4 sglFsSkybox(const SglFsCtx &c, const float *v) {
     V2 uv = v2(atan2f(dir.z, dir.x), asinf(-dir.y));
     uv = v2(uv.x * 0.1591f + 0.5f, uv.y * 0.3183f + 0.5f);
     return sglTexture2D(sglSlot(c, SGL_SLOT_SKY_EQUIRECT), uv, 0.f);   // no lodFunc installed for the skybox sampler
+  }
+  if ((c.draw->fastSamplers >> SGL_SLOT_SKY_CUBE) & 1u) {
+    // "simple" cube (linear RGBA8, LINEAR filter): the same bilinear footprint through the branch-free split-phase tap
+    int face;
+    float fu, fv;
+    sglCubeFaceT<true>(wp.x, wp.y, wp.z, face, fu, fv);
+    const SglSamplerSlot &b = c.draw->samplers[SGL_SLOT_SKY_CUBE];
+    return sglUnpackRGBA(sglTapMix(sglTapIssue(sglTapView(&c.textures[b.tex], face, 0, b.wrap), fu, fv)));
   }
   return sglTextureCube(sglSlot(c, SGL_SLOT_SKY_CUBE), wp, 0.f);
 }
