@@ -342,8 +342,8 @@ int sgl_init(int device_ordinal, int rank, int world) {
     int lo = 0, hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CU(cudaStreamCreateWithPriority(&g.geomStream, cudaStreamNonBlocking, hi));
+    CU(cudaStreamCreateWithPriority(&g.auxStream, cudaStreamNonBlocking, hi));   // small kernels next to a visibility kernel
   }
-  CU(cudaStreamCreateWithFlags(&g.auxStream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&g.auxReady, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&g.auxDone, cudaEventDisableTiming));
   CU(cudaStreamCreateWithFlags(&g.copyStream, cudaStreamNonBlocking));
