@@ -205,8 +205,8 @@ def main():
         gather = args.gather
         if gather == "p2p":
             try:
-                store = M.PeerFrameStore(lib, WIDTH, HEIGHT, rank, world, frames_per_slot=1 if tiles else world, slots=2,
-                                         control_group=ctl)
+                store = M.PeerFrameStore(lib, WIDTH, HEIGHT, rank, world, frames_per_slot=1 if tiles else world, slots=4,
+                                         control_group=ctl, lag=2)
             except RuntimeError as e:      # CUDA IPC not permitted on this box (all ranks agree): NCCL moves the same bytes
                 gather = "nccl (p2p unavailable: %s)" % str(e)[:80]
         if store is None and not tiles:
@@ -247,6 +247,16 @@ def main():
 
     g_d2h = [0]
 
+    def flush_store(e2e):
+        if store is None:
+            return
+        consume = None
+        if e2e and tiles and rank == 0:
+            def consume(ptr):
+                host_all.copy_(M.device_view(ptr, nbytes), non_blocking=True)
+                g_d2h[0] += nbytes
+        store.flush(consume)
+
     def sync_all():
         capi.check(lib.sgl_wait_idle())
         torch.cuda.synchronize()
@@ -255,12 +265,14 @@ def main():
 
     for _ in range(W):
         step(False)
+    flush_store(False)
     sync_all()
     # CPU cost of recording + submitting one frame, measured on a short burst that cannot fill the launch queue
     h0 = time.perf_counter()
     for _ in range(8):
         step(False)
     host_submit_ms = (time.perf_counter() - h0) * 1e3 / 8
+    flush_store(False)
     sync_all()
 
     # ---- timed region 1: device-resident throughput (CUDA events on the library's stream), max over ranks
@@ -271,6 +283,7 @@ def main():
         capi.check(lib.sgl_timer_begin())
         for _ in range(K):
             step(False)
+        flush_store(False)
         capi.check(lib.sgl_timer_end(ms))
         sync_all()
         elapsed_ms = _max_over_ranks(ms.value, world)
@@ -285,6 +298,7 @@ def main():
     t0 = time.perf_counter()
     for _ in range(K):
         step(True)
+    flush_store(True)
     sync_all()
     e2e_s = _max_over_ranks(time.perf_counter() - t0, world)
     ctr2 = capi.counters()
@@ -298,6 +312,7 @@ def main():
     capi.check(lib.sgl_set_profiling(1))
     for _ in range(20):
         step(False)
+    flush_store(False)
     capi.check(lib.sgl_wait_idle())
     ktimes = capi.kernel_times()
     capi.check(lib.sgl_set_profiling(0))

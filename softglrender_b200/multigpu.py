@@ -168,17 +168,22 @@ class PeerFrameStore:
 
       producer r, frame f:  wait(consumed[r] >= f - slots + 1)  ->  render (mirror = slot f % slots)  ->  signal(done[r] = f + 1)
       rank 0,     frame f:  wait(done[0..world) >= f + 1)        ->  consume                           ->  signal(consumed[r] = f + 1) for all r
+                            (with lag > 0 rank 0 does this for frame f - lag while frame f renders)
 
     ``consumed`` flags live in each producer's own memory (rank 0 maps them), ``done`` flags in rank 0's, so every spin
     reads local HBM and every signal is one remote store.
     """
     FLAG_STRIDE = 64
 
-    def __init__(self, lib, width, height, rank, world, frames_per_slot, slots=2, control_group=None, timeout_ms=2000):
+    def __init__(self, lib, width, height, rank, world, frames_per_slot, slots=2, control_group=None, timeout_ms=2000, lag=0):
         import torch
         import torch.distributed as dist
         from . import capi
         self.lib, self.rank, self.world, self.slots, self.fps, self.timeout_ms = lib, rank, world, slots, frames_per_slot, timeout_ms
+        # rank 0 collects frame f - lag while everybody renders frame f: per-frame jitter between the ranks is absorbed
+        # instead of pacing all of them on the slowest one each frame (0 <= lag <= slots - 1; flush() drains the tail)
+        self.lag = max(0, min(lag, slots - 1))
+        self.collected = 0
         self.frame_bytes = width * height * 4
         self.header = self.FLAG_STRIDE * max(world, 1)
         store_bytes = self.header + self.frame_bytes * frames_per_slot * slots
@@ -241,13 +246,25 @@ class PeerFrameStore:
         from . import capi
         f = self.frame_no
         capi.check(self.lib.sgl_peer_signal(self.store.value + self.FLAG_STRIDE * self.rank, f + 1))
-        if self.rank == 0:
-            capi.check(self.lib.sgl_peer_wait(self.store.value, self.world, f + 1, self.timeout_ms))
-            if consume is not None:
-                consume(self.slot_ptr(f, 0))
-            for r in range(1, self.world):
-                capi.check(self.lib.sgl_peer_signal(self.peer_flags[r], f + 1))
         self.frame_no = f + 1
+        if self.rank == 0 and f - self.lag >= self.collected:
+            self._collect(f - self.lag, consume)
+
+    def _collect(self, upto, consume):
+        from . import capi
+        while self.collected <= upto:
+            c = self.collected
+            capi.check(self.lib.sgl_peer_wait(self.store.value, self.world, c + 1, self.timeout_ms))
+            if consume is not None:
+                consume(self.slot_ptr(c, 0))
+            for r in range(1, self.world):
+                capi.check(self.lib.sgl_peer_signal(self.peer_flags[r], c + 1))
+            self.collected = c + 1
+
+    def flush(self, consume=None):
+        """Rank 0: collect every frame submitted so far (end of a batch / of a timed region)."""
+        if self.rank == 0:
+            self._collect(self.frame_no - 1, consume)
 
     def timeouts(self):
         from . import capi

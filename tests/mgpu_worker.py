@@ -86,20 +86,23 @@ def main():
 
         # (c) frame-parallel + direct peer stores: every rank renders the whole frame into its slot of rank 0's store
         capi.check(lib.sgl_set_tile_owner_map(None, 0, 0))
-        store2 = M.PeerFrameStore(lib, w, h, rank, world, frames_per_slot=world, slots=2, control_group=ctl)
+        # (4 slots, rank 0 collects two frames behind the renderers and drains the tail with flush())
+        store2 = M.PeerFrameStore(lib, w, h, rank, world, frames_per_slot=world, slots=4, control_group=ctl, lag=2)
         got = []
-        for f in range(3):
+        for f in range(7):
             store2.begin_frame(tex, rank)
             p.frame(sync=False)
 
             def consume2(ptr):
                 got.append(M.device_view(ptr, world * w * h * 4).clone())
             store2.end_frame(consume2 if rank == 0 else None)
+        store2.flush(consume2 if rank == 0 else None)
         capi.check(lib.sgl_wait_idle())
         torch.cuda.synchronize()
         dist.barrier()
         assert store2.timeouts() == 0
         if rank == 0:
+            assert len(got) == 7
             for t in got:
                 a = t.cpu().numpy().reshape(world, h, w, 4)
                 for r in range(world):
