@@ -330,7 +330,7 @@ def main():
                     "d2h_bytes_per_step": d2h // K},
             "gpu_launches": launches, "clocks": clocks_summary, "host_submit_ms_per_step": host_submit_ms}
     if rank == 0:
-        line["roofline"] = roofline_block(ktimes, ctr, K, data)
+        line["roofline"] = roofline_block(ktimes, ctr, K)
         line["kernel_ms_per_frame"] = {k: v[1] / 20.0 for k, v in sorted(ktimes.items())}
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -377,7 +377,7 @@ def _max_over_ranks(v, world):
     return float(t.item())
 
 
-def roofline_block(ktimes, ctr, K, data_dir):
+def roofline_block(ktimes, ctr, K):
     """Roofline of the dominant kernel (largest share of the step; DESIGN.md section 6 states the per-unit figures).
 
     Algorithmic bytes per launch = what the kernel must move once, with perfect reuse:

@@ -1,10 +1,13 @@
-// sm_100a kernels of RendererCUDA.  One render pass = 5 launches:
+// sm_100a kernels of RendererCUDA.  Geometry stage of a pass:
 //   sglVertexKernel   vertex shading + clip mask + perspective divide + viewport, one thread per VAO vertex
 //   sglSetupKernel    assembly, clipping (VS re-execution), culling, primitive setup, tile counting
-//   sglTileScanKernel exclusive scan of per-tile counts (single CTA)
+//   sglTileScanKernel exclusive scan of per-tile counts + heavy-first tile classes (single CTA)
 //   sglBinFillKernel  scatter primitive slots into per-tile lists
-//   sglRasterKernel   one CTA per 16x16 screen tile: order-sort the tile's list in shared memory, per-pixel
-//                     coverage/depth in registers, deferred shading, blend, MSAA resolve, write-back
+// Pixel stage: the deferred pair sglVisKernel / sglShadeKernel (sgl_vis.cuh) for opaque draws, or
+//   sglRasterKernel   the fused ordered form for blending and for lines/points of programs with varyings: one CTA per
+//                     16x16 tile, order-sorted list, coverage/depth in registers, immediate shading + blend for blended
+//                     fragments, deferred owners for opaque ones, MSAA resolve, write-back
+// plus the depth-only kernels of sgl_depth.cuh, upload/utility kernels and the multi-GPU gather helpers.
 #pragma once
 #include <cuda_runtime.h>
 #include "sgl_pixel.h"
@@ -194,25 +197,6 @@ __global__ void __launch_bounds__(256) sglBinFillKernel(SglPassParams P) {
 #endif
 #define SGL_PRIM_BATCH 64
 
-__device__ __forceinline__ void sglBitonicSort(uint32_t *keys, uint32_t *vals, int n /* power of two */) {
-  for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        int ixj = i ^ j;
-        if (ixj > i) {
-          uint32_t a = keys[i], b = keys[ixj];
-          bool up = (i & k) == 0;
-          if ((a > b) == up) {
-            keys[i] = b; keys[ixj] = a;
-            uint32_t t = vals[i]; vals[i] = vals[ixj]; vals[ixj] = t;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
 template<int NS>
 __global__ void __launch_bounds__(SGL_TILE_THREADS) sglRasterKernel(SglPassParams P) {
   __shared__ uint32_t sKeys[SGL_SORT_CAP];
@@ -221,10 +205,13 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS) sglRasterKernel(SglPassParam
   __shared__ int sCount;
   __shared__ unsigned int sShaded;
 
-  const int tile = blockIdx.x;
-  if (P.tileOwner && P.tileOwner[tile] != P.rank) return;
+  int quarter;
+  const int tile = sglTileOfBlock(P, blockIdx.x, 0, quarter);   // heavy tiles first
+  if (tile < 0) return;
   const int tx = tile % P.tilesX, ty = tile / P.tilesX;
   const int tid = threadIdx.x;
+  // a warp = a 16x2 pixel strip: this kernel mostly sees few, large (blended) primitives, where the row-major strip's
+  // 64-byte colour segments beat the 8x4 block + warp-level cull of the visibility kernel (measured on config 3)
   const int px = tx * SGL_TILE + (tid & (SGL_TILE - 1));
   const int py = ty * SGL_TILE + (tid / SGL_TILE);
   const bool inFb = px < P.fbW && py < P.fbH;
@@ -298,13 +285,7 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS) sglRasterKernel(SglPassParam
     const int n = sCount;
     if (P.skipEmptyTiles && !loaded && n == 0 && hi == keyEnd) return;   // nothing touches this tile: it keeps its content
     loadState();
-    if (n > 1) {
-      int n2 = 1;
-      while (n2 < n) n2 <<= 1;
-      for (int i = n + tid; i < n2; i += SGL_TILE_THREADS) { sKeys[i] = 0xFFFFFFFFu; sSlots[i] = 0; }
-      __syncthreads();
-      sglBitonicSort(sKeys, sSlots, n2);
-    }
+    sglSortTileList(sKeys, sSlots, n);
     // ---- process in order
     for (int b0 = 0; b0 < n; b0 += SGL_PRIM_BATCH) {
       int nb = n - b0 < SGL_PRIM_BATCH ? n - b0 : SGL_PRIM_BATCH;

@@ -481,25 +481,52 @@ SGL_HD float sglFxaaQuality(int i) {
   return q < 5.f ? 1.0f : (q > 5.f ? (q < 10.f ? 2.0f : (q < 11.f ? 4.0f : 8.0f)) : 1.5f);
 }
 
+// screen-texture fetch of the FXAA pass: the split-phase tap when the sampler is "simple" (linear RGBA8, LINEAR filter:
+// what the Viewer binds), the generic sampler otherwise -- same footprint, same truncating mixes
+struct SglFxaaTex {
+  SglSampler s;
+  SglTapView tv;
+  bool fast;
+  SGL_HD V4 fetch(V2 uv, int ox, int oy) const {
+    if (fast) return sglUnpackRGBA(sglTapMix(sglTapIssue(tv, uv.x, uv.y, ox, oy)));
+    return sglTexture2DOffset(s, uv, 0.f, ox, oy);
+  }
+};
+
 SGL_HD V4 sglFsFxaa(const SglFsCtx &c, const float *v) {
   const SglDrawRec &d = *c.draw;
-  SglSampler s = sglSlot(c, SGL_SLOT_FXAA_SCREEN);
+  SglFxaaTex s;
+  s.s = sglSlot(c, SGL_SLOT_FXAA_SCREEN);
+  s.fast = ((d.fastSamplers >> SGL_SLOT_FXAA_SCREEN) & 1u) != 0;
+  s.tv = sglTapView(&c.textures[s.fast ? d.samplers[SGL_SLOT_FXAA_SCREEN].tex : 0], 0, 0, d.samplers[SGL_SLOT_FXAA_SCREEN].wrap);
   V2 uv = v2(v[0], v[1]);
   V2 inv = v2(1.0f / uF(d, 0), 1.0f / uF(d, 4));
-  V4 colorCenter = sglTexture2D(s, uv, 0.f);
+  V4 colorCenter;
+  float lumaDown, lumaUp, lumaLeft, lumaRight;
+  if (s.fast) {   // the five taps of the early-out test in flight together
+    SglTap tc = sglTapIssue(s.tv, uv.x, uv.y), td = sglTapIssue(s.tv, uv.x, uv.y, 0, -1), tu = sglTapIssue(s.tv, uv.x, uv.y, 0, 1);
+    SglTap tl = sglTapIssue(s.tv, uv.x, uv.y, -1, 0), tr = sglTapIssue(s.tv, uv.x, uv.y, 1, 0);
+    colorCenter = sglUnpackRGBA(sglTapMix(tc));
+    lumaDown = sglLuma(sglUnpackRGBA(sglTapMix(td)));
+    lumaUp = sglLuma(sglUnpackRGBA(sglTapMix(tu)));
+    lumaLeft = sglLuma(sglUnpackRGBA(sglTapMix(tl)));
+    lumaRight = sglLuma(sglUnpackRGBA(sglTapMix(tr)));
+  } else {
+    colorCenter = s.fetch(uv, 0, 0);
+    lumaDown = sglLuma(s.fetch(uv, 0, -1));
+    lumaUp = sglLuma(s.fetch(uv, 0, 1));
+    lumaLeft = sglLuma(s.fetch(uv, -1, 0));
+    lumaRight = sglLuma(s.fetch(uv, 1, 0));
+  }
   float lumaCenter = sglLuma(colorCenter);
-  float lumaDown = sglLuma(sglTexture2DOffset(s, uv, 0.f, 0, -1));
-  float lumaUp = sglLuma(sglTexture2DOffset(s, uv, 0.f, 0, 1));
-  float lumaLeft = sglLuma(sglTexture2DOffset(s, uv, 0.f, -1, 0));
-  float lumaRight = sglLuma(sglTexture2DOffset(s, uv, 0.f, 1, 0));
   float lumaMin = fminf(lumaCenter, fminf(fminf(lumaDown, lumaUp), fminf(lumaLeft, lumaRight)));
   float lumaMax = fmaxf(lumaCenter, fmaxf(fmaxf(lumaDown, lumaUp), fmaxf(lumaLeft, lumaRight)));
   float lumaRange = lumaMax - lumaMin;
   if (lumaRange < fmaxf(0.0312f, lumaMax * 0.125f)) return v4(colorCenter.x, colorCenter.y, colorCenter.z, 1.f);
-  float lumaDownLeft = sglLuma(sglTexture2DOffset(s, uv, 0.f, -1, -1));
-  float lumaUpRight = sglLuma(sglTexture2DOffset(s, uv, 0.f, 1, 1));
-  float lumaUpLeft = sglLuma(sglTexture2DOffset(s, uv, 0.f, -1, 1));
-  float lumaDownRight = sglLuma(sglTexture2DOffset(s, uv, 0.f, 1, -1));
+  float lumaDownLeft = sglLuma(s.fetch(uv, -1, -1));
+  float lumaUpRight = sglLuma(s.fetch(uv, 1, 1));
+  float lumaUpLeft = sglLuma(s.fetch(uv, -1, 1));
+  float lumaDownRight = sglLuma(s.fetch(uv, 1, -1));
   float lumaDownUp = lumaDown + lumaUp;
   float lumaLeftRight = lumaLeft + lumaRight;
   float lumaLeftCorners = lumaDownLeft + lumaUpLeft;
@@ -535,11 +562,11 @@ SGL_HD V4 sglFsFxaa(const SglFsCtx &c, const float *v) {
   bool reached1 = false, reached2 = false, reachedBoth = false;
   for (int i = 1; i < 12; i++) {
     if (!reached1) {
-      lumaEnd1 = sglLuma(sglTexture2D(s, uv1, 0.f)) - lumaLocalAverage;
+      lumaEnd1 = sglLuma(s.fetch(uv1, 0, 0)) - lumaLocalAverage;
       reached1 = fabsf(lumaEnd1) >= gradientScaled;
     }
     if (!reached2) {
-      lumaEnd2 = sglLuma(sglTexture2D(s, uv2, 0.f)) - lumaLocalAverage;
+      lumaEnd2 = sglLuma(s.fetch(uv2, 0, 0)) - lumaLocalAverage;
       reached2 = fabsf(lumaEnd2) >= gradientScaled;
     }
     reachedBoth = reached1 && reached2;
@@ -567,7 +594,7 @@ SGL_HD V4 sglFsFxaa(const SglFsCtx &c, const float *v) {
   V2 finalUv = uv;
   if (isHorizontal) finalUv.y += finalOffset * stepLength;
   else finalUv.x += finalOffset * stepLength;
-  V4 fc = sglTexture2D(s, finalUv, 0.f);
+  V4 fc = s.fetch(finalUv, 0, 0);
   return v4(fc.x, fc.y, fc.z, 1.f);
 }
 

@@ -298,8 +298,8 @@ SGL_HD int sglTapWrap(int x, int n, bool clamp) {
   int c = x < 0 ? 0 : (x >= n ? n - 1 : x);
   return clamp ? c : r;
 }
-SGL_HD SglTap sglTapIssue(const SglTapView &t, float u, float v) {   // uv normalised
-  float tu = xsub(xadd(xmul(u, (float) t.w), 0.f), 0.5f), tv = xsub(xadd(xmul(v, (float) t.h), 0.f), 0.5f);
+SGL_HD SglTap sglTapIssue(const SglTapView &t, float u, float v, int ox = 0, int oy = 0) {   // uv normalised, texel offset
+  float tu = xsub(xadd(xmul(u, (float) t.w), (float) ox), 0.5f), tv = xsub(xadd(xmul(v, (float) t.h), (float) oy), 0.5f);
   float fu = floorf(tu), fv = floorf(tv);
   int x0 = (int) fu, y0 = (int) fv;
   int xa = sglTapWrap(x0, t.w, t.clamp), xb = sglTapWrap(x0 + 1, t.w, t.clamp);

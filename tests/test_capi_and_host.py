@@ -92,7 +92,6 @@ def test_uniform_packing_sizes():
     from softglrender_b200.scene import viewer
     m = np.eye(4, dtype=np.float32)
     assert len(viewer.pack_uniforms_model(True, m, m, np.eye(3), m)) == 256
-    assert len(viewer.pack_uniforms_scene((0, 0, 0),) * 1 + b"") == 64 if False else True
     assert len(viewer.pack_uniforms_scene((0, 0, 0), (1, 1, 1), (2, 2, 2), (3, 3, 3))) == 64
     b = viewer.pack_uniforms_material(True, False, True, 10.0, 0.5, (1, 2, 3, 4))
     assert len(b) == 48 and struct.unpack_from("<f", b, 12)[0] == 10.0 and struct.unpack_from("<4f", b, 32) == (1, 2, 3, 4)

@@ -18,7 +18,8 @@ capi.check(lib.sgl_get_tile_list_sizes(None, 0, C.byref(tx), C.byref(ty)))
 a = np.zeros(tx.value * ty.value, np.uint32)
 capi.check(lib.sgl_get_tile_list_sizes(a.ctypes.data, a.size, None, None))
 a = a.reshape(ty.value, tx.value)
-print("tiles", a.shape, "sum", int(a[a != 0xFFFFFFFF].sum()), "overflow tiles", int((a == 0xFFFFFFFF).sum()))
+print("tiles", a.shape, "prepared (heavy) lists: sum", int(a[a != 0xFFFFFFFF].sum()), "; tiles without a prepared list (light, or overflow):", int((a == 0xFFFFFFFF).sum()))
+a = np.where(a == 0xFFFFFFFF, 0, a)
 v = np.sort(a[a != 0xFFFFFFFF].ravel())[::-1]
 print("top 30:", v[:30].tolist())
 print("percentiles 50/90/99/99.9:", [int(np.percentile(v, q)) for q in (50, 90, 99, 99.9)])
