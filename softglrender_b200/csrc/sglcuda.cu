@@ -84,7 +84,7 @@ struct Ctx {
   int tileTiming = 0;
   const uint32_t *lastTileSortedCount = nullptr;   // of the most recent non-depth-only pass (instrumentation)
   int lastTilesX = 0, lastTilesY = 0;
-  cudaStream_t geomStream = nullptr;
+  cudaStream_t geomStreams[3] = {nullptr, nullptr, nullptr};   // one per arena slot: geometry stages of consecutive passes are independent
   // depth-only passes (shadow maps) run their pixel stage on an auxiliary stream: they start when all earlier pixel work
   // is done and only the next kernel that SAMPLES textures (or touches their depth texture) waits for them, so the
   // shadow pass of a frame overlaps the visibility kernel of its main pass
@@ -189,7 +189,7 @@ uint8_t *levelPtr(const TextureRec &t, int layer, int level) {
 
 int syncAll() {
   CU(cudaStreamSynchronize(g.stream));
-  if (g.geomStream) CU(cudaStreamSynchronize(g.geomStream));
+  for (cudaStream_t gs : g.geomStreams) if (gs) CU(cudaStreamSynchronize(gs));
   if (g.auxStream) CU(cudaStreamSynchronize(g.auxStream));
   g.auxPending = false;
   return SGL_OK;
@@ -341,7 +341,7 @@ int sgl_init(int device_ordinal, int rank, int world) {
   {  // geometry kernels are small and feed the pixel stage of the NEXT pass: give them priority over resident pixel work
     int lo = 0, hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CU(cudaStreamCreateWithPriority(&g.geomStream, cudaStreamNonBlocking, hi));
+    for (auto &gs : g.geomStreams) CU(cudaStreamCreateWithPriority(&gs, cudaStreamNonBlocking, hi));
     CU(cudaStreamCreateWithPriority(&g.auxStream, cudaStreamNonBlocking, hi));   // small kernels next to a visibility kernel
   }
   CU(cudaEventCreateWithFlags(&g.auxReady, cudaEventDisableTiming));
@@ -379,7 +379,7 @@ int sgl_init(int device_ordinal, int rank, int world) {
 int sgl_shutdown(void) {
   if (!g.ready) return SGL_OK;
   cudaStreamSynchronize(g.stream);
-  if (g.geomStream) cudaStreamSynchronize(g.geomStream);
+  for (cudaStream_t gs : g.geomStreams) if (gs) cudaStreamSynchronize(gs);
   for (auto &b : g.buffers)
     if (b.d) cudaFree(b.d);
   if (g.copyStream) cudaStreamSynchronize(g.copyStream);
@@ -396,7 +396,7 @@ int sgl_shutdown(void) {
     if (a.geomDone) cudaEventDestroy(a.geomDone);
     if (a.pixelDone) cudaEventDestroy(a.pixelDone);
   }
-  if (g.geomStream) cudaStreamDestroy(g.geomStream);
+  for (cudaStream_t gs : g.geomStreams) if (gs) cudaStreamDestroy(gs);
   if (g.auxStream) { cudaStreamSynchronize(g.auxStream); cudaStreamDestroy(g.auxStream); }
   if (g.auxReady) cudaEventDestroy(g.auxReady);
   if (g.auxDone) cudaEventDestroy(g.auxDone);
@@ -491,7 +491,7 @@ int sgl_set_profiling(int on) {
 int sgl_get_kernel_times(SglKernelTime *out, int capacity) {
   if (!g.ready) return 0;
   cudaStreamSynchronize(g.stream);
-  if (g.geomStream) cudaStreamSynchronize(g.geomStream);
+  for (cudaStream_t gs : g.geomStreams) if (gs) cudaStreamSynchronize(gs);
   int n = 0;
   const bool dump = getenv("SGL_PROFILE_OVERLAP") != nullptr && !gProf.empty();
   for (auto &p : gProf) {
@@ -947,6 +947,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   size_t oTileSortedCount = depthOnly ? 0 : take(sizeof(uint32_t) * nTiles);
   size_t oTileOrder = depthOnly ? 0 : take(sizeof(uint32_t) * nTiles * SGL_TILE_CLASSES);
   Ctx::Arena &arena = g.arenas[g.arenaNext];
+  const cudaStream_t geomStream = g.geomStreams[g.arenaNext];
   g.arenaNext = (g.arenaNext + 1) % 3;
   int rc = ensureArena(arena, off);
   if (rc) return rc;
@@ -956,11 +957,11 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   static const bool profileOverlapped = getenv("SGL_PROFILE_OVERLAP") != nullptr;   // timeline dumps (development)
   const bool overlap = !g.noOverlap && (!gProfiling || profileOverlapped);
   struct StageGuard { ~StageGuard() { gCur = nullptr; } } stageGuard;
-  gCur = overlap ? g.geomStream : g.stream;
-  if (arena.used && overlap) CU(cudaStreamWaitEvent(g.geomStream, arena.pixelDone, 0));
+  gCur = overlap ? geomStream : g.stream;
+  if (arena.used && overlap) CU(cudaStreamWaitEvent(geomStream, arena.pixelDone, 0));
   auto toPixelStage = [&]() -> int {   // everything issued so far on the geometry stream precedes what follows
     if (gCur != g.stream) {
-      CU(cudaEventRecord(arena.geomDone, g.geomStream));
+      CU(cudaEventRecord(arena.geomDone, geomStream));
       CU(cudaStreamWaitEvent(g.stream, arena.geomDone, 0));
     }
     gCur = g.stream;
@@ -1049,7 +1050,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     if (aux) {
       CU(cudaEventRecord(g.auxReady, g.stream));           // all earlier pixel work (it may sample this depth texture) first
       CU(cudaStreamWaitEvent(g.auxStream, g.auxReady, 0));
-      CU(cudaEventRecord(arena.geomDone, g.geomStream));
+      CU(cudaEventRecord(arena.geomDone, geomStream));
       CU(cudaStreamWaitEvent(g.auxStream, arena.geomDone, 0));
       gCur = g.auxStream;
     } else {
