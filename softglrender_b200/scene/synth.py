@@ -322,3 +322,97 @@ def soup_trace(n_tris=100000, width=1920, height=1080, seed=0x5EED, n_textures=8
     w.readback(color, "color")
     w.readback(depth, "depth")
     return w
+
+
+def edge_trace(msaa=False):
+    """Degenerate inputs the API must take in its stride: a render pass without draws (clear only), a draw with no
+    indices, a 1x1 and a 3x2 framebuffer, a viewport smaller than / offset inside the framebuffer's tile grid, a pass
+    that loads (no clear) what the previous pass wrote, degenerate (zero-area) and fully clipped triangles, a
+    depth-only pass with zero primitives, and a blended draw as the FIRST draw of a pass."""
+    w = T.TraceWriter()
+    eye4 = np.eye(4, dtype=np.float32)
+    MB, TB = T.UniformBlock_Model, T.UniformBlock_Material
+    b_model = w.create_block("UniformsModel", 256)
+    b_mat = w.create_block("UniformsMaterial", 48)
+    w.block_data(b_model, pack_uniforms_model(False, eye4, eye4, np.eye(3), eye4))
+    prog = w.create_program(T.Shading_BaseColor, [])
+    rs = T.RenderStates()
+    rs.depthTest = True
+    rs.cullFace = False
+    pipe = w.create_pipeline(rs)
+    rb = T.RenderStates()
+    rb.depthTest = False
+    rb.cullFace = False
+    rb.blend = True
+    rb.set_blend_factor(T.BlendFactor_SRC_ALPHA, T.BlendFactor_ONE_MINUS_SRC_ALPHA)
+    pipe_blend = w.create_pipeline(rb)
+    tri = _verts(np.array([(-0.8, -0.7, 0.2), (0.9, -0.6, 0.4), (0.1, 0.8, 0.6)], np.float32))
+    big = _verts(np.array([(-3, -3, 0.5), (3, -3, 0.5), (0, 3, 0.5)], np.float32))
+    degenerate = _verts(np.array([(-0.5, -0.5, 0.3), (0.5, 0.5, 0.3), (0.0, 0.0, 0.3),        # zero area
+                                  (5, 5, 0.5), (6, 5, 0.5), (5, 6, 0.5)], np.float32))          # outside the frustum
+    vao_tri = w.create_vao(tri, np.arange(3, dtype=np.int32))
+    vao_big = w.create_vao(big, np.arange(3, dtype=np.int32))
+    vao_deg = w.create_vao(degenerate, np.arange(6, dtype=np.int32))
+    vao_empty = w.create_vao(tri, np.zeros(0, np.int32))
+    outs = []
+
+    def target(wd, ht, tag):
+        c = w.create_texture(wd, ht, T.TextureType_2D, T.TextureFormat_RGBA8,
+                             T.TextureUsage_AttachmentColor | T.TextureUsage_RendererOutput, False, msaa)
+        w.tex_init(c)
+        d = w.create_texture(wd, ht, T.TextureType_2D, T.TextureFormat_FLOAT32, T.TextureUsage_AttachmentDepth, False, msaa)
+        w.tex_init(d)
+        f = w.create_fbo(False)
+        w.fbo_color(f, c, 0)
+        w.fbo_depth(f, d)
+        outs.append((c, "color_" + tag))
+        outs.append((d, "depth_" + tag))
+        return f
+
+    def draw(vao, base, p=None):
+        w.block_data(b_mat, pack_uniforms_material(False, False, False, 1.0, 1.0, base))
+        w.draw(vao, prog, p if p is not None else pipe, {MB: b_model, TB: b_mat}, {})
+
+    f_clear, f_1x1, f_3x2, f_vp, f_load = target(70, 50, "clear"), target(1, 1, "1x1"), target(3, 2, "3x2"), target(100, 60, "vp"), target(64, 64, "load")
+    d_only = w.create_texture(40, 40, T.TextureType_2D, T.TextureFormat_FLOAT32, T.TextureUsage_AttachmentDepth, False, False)
+    w.tex_init(d_only)
+    f_depth = w.create_fbo(False)
+    w.fbo_depth(f_depth, d_only)
+    outs.append((d_only, "depth_only_empty"))
+
+    w.frame_begin()
+    w.begin_pass(f_clear, True, True, (0.2, 0.4, 0.6, 0.8), 1.0)          # no draws: clear only
+    w.viewport(0, 0, 70, 50)
+    w.end_pass()
+    w.begin_pass(f_1x1, True, True, (0, 0, 0, 1), 1.0)
+    w.viewport(0, 0, 1, 1)
+    draw(vao_big, (1.0, 0.5, 0.25, 1.0))
+    draw(vao_empty, (0, 1, 0, 1))                                         # indexCount == 0
+    w.end_pass()
+    w.begin_pass(f_3x2, True, True, (0, 0, 0, 1), 1.0)
+    w.viewport(0, 0, 3, 2)
+    draw(vao_tri, (0.3, 0.6, 0.9, 1.0))
+    draw(vao_deg, (1, 0, 0, 1))                                           # zero-area + fully clipped
+    w.end_pass()
+    w.begin_pass(f_vp, True, True, (0.05, 0.05, 0.05, 1), 1.0)           # viewport smaller than the framebuffer
+    w.viewport(0, 0, 37, 23)
+    draw(vao_tri, (0.9, 0.8, 0.1, 1.0))
+    w.end_pass()
+    w.begin_pass(f_load, True, True, (0.1, 0.1, 0.1, 1), 1.0)
+    w.viewport(0, 0, 64, 64)
+    draw(vao_tri, (0.2, 0.9, 0.4, 1.0))
+    w.end_pass()
+    w.begin_pass(f_load, False, False, (0, 0, 0, 0), 1.0)                 # loads colour + depth; blended draw comes FIRST
+    w.viewport(0, 0, 64, 64)
+    draw(vao_big, (1.0, 0.2, 0.2, 0.5), pipe_blend)
+    draw(vao_tri, (0.1, 0.1, 0.9, 1.0))
+    w.end_pass()
+    w.begin_pass(f_depth, False, True, (0, 0, 0, 0), 1.0)                 # depth-only pass, nothing to rasterise
+    w.viewport(0, 0, 40, 40)
+    draw(vao_deg, (0, 0, 0, 1))
+    w.end_pass()
+    w.frame_end()
+    w.wait_idle()
+    for t, tag in outs:
+        w.readback(t, tag)
+    return w
