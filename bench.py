@@ -123,7 +123,17 @@ def cpu_reference_fps(trace, data_dir, frames, warmup):
             "sample": "%d timed frames of the same config-2 trace (median), %d warm-up, %.0f s wall" % (frames, warmup, time.time() - t0)}
 
 
+def _json_only_stdout():
+    """The contract is ONE JSON line on stdout: everything else a library may print there (NCCL's version banner, ...) is
+    sent to stderr by pointing fd 1 at fd 2; the returned writer is the original stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def main():
+    out = _json_only_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -132,8 +142,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mgpu", default="frames", choices=["frames", "tiles"],
                     help="N > 1: frame-parallel (weak scaling, default) or one frame sharded by screen tiles (strong scaling)")
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
-                    help="N > 1: finished pixels reach rank 0 by direct peer stores from the shading kernel, or by an NCCL gather")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "dma", "nccl"],
+                    help="N > 1: finished pixels reach rank 0 by direct peer stores from the shading kernel (p2p), by copy-engine "
+                         "pushes of whole frames into rank 0's store (dma; frame-parallel only), or by an NCCL gather")
     args = ap.parse_args()
     rank, local_rank, world = _env_rank()
     K, W = args.steps, max(args.warmup, 3)
@@ -161,7 +172,8 @@ def main():
                 "data": "bundled glTF asset + synthetic camera (Config defaults)", "config": config, "impl": "reference",
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        out.write(json.dumps(line) + "\n")
+        out.flush()
         return 0
 
     # ---------------------------------------------------------------------------------------------- RendererCUDA arm
@@ -203,10 +215,12 @@ def main():
             tile_gather = M.TileGather(WIDTH, HEIGHT, rank, world, "interleave")
             tile_gather.install(lib)
         gather = args.gather
-        if gather == "p2p":
+        if gather == "dma" and tiles:
+            gather = "p2p"
+        if gather in ("p2p", "dma"):
             try:
                 store = M.PeerFrameStore(lib, WIDTH, HEIGHT, rank, world, frames_per_slot=1 if tiles else world, slots=4,
-                                         control_group=ctl, lag=2)
+                                         control_group=ctl, lag=2, dma=(gather == "dma"))
             except RuntimeError as e:      # CUDA IPC not permitted on this box (all ranks agree): NCCL moves the same bytes
                 gather = "nccl (p2p unavailable: %s)" % str(e)[:80]
         if store is None and not tiles:
@@ -218,8 +232,10 @@ def main():
                              ("sort-first screen-tile ownership x%d (16x16 tiles, 4x4-tile blocks interleaved), geometry replicated" % world
                               if tiles else "frame-parallel x%d (every rank renders its own frame each step)" % world))
     config["gather"] = ("n/a" if world == 1 else
-                        ("direct peer stores: the shading kernel writes resolved pixels into rank 0's HBM over NVLink (CUDA IPC), "
-                         "stream-ordered system-scope flags" if store is not None else
+                        (("copy-engine pushes of finished frames into rank 0's HBM over NVLink (CUDA IPC), stream-ordered system-scope flags"
+                          if store.dma else
+                          "direct peer stores: the shading kernel writes resolved pixels into rank 0's HBM over NVLink (CUDA IPC), "
+                          "stream-ordered system-scope flags") if store is not None else
                          "NCCL gather to rank 0 (%s)" % gather))
     step_no = [0]
 
@@ -337,7 +353,8 @@ def main():
                 line["cpu_baseline"] = cpu_reference_fps(trace, data, 40, 2)
             except Exception as e:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"error": str(e)[:200]}
-        print(json.dumps(line))
+        out.write(json.dumps(line) + "\n")
+        out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

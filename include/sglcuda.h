@@ -153,7 +153,8 @@ int sgl_texture_gen_mips(int handle);                                   /* Sampl
 /* kind 0: attachment (w*h*samples*4 bytes, [y][x][sample]); kind 1: resolved colour of an MS texture */
 int sgl_texture_readback(int handle, int layer, int level, int kind, void *host_out, size_t bytes);
 /* pipelined form: queued behind all submitted work on a second stream; a later pass that overwrites the image waits for
- * the copy on the device, the host waits with sgl_readback_wait() (or sgl_wait_idle()).  host_out should be pinned. */
+ * the copy on the device, the host waits with sgl_readback_wait() (or sgl_wait_idle()).  host_out should be pinned host
+ * memory, or device memory (also a peer GPU's, mapped with sgl_peer_open). */
 int sgl_texture_readback_async(int handle, int layer, int level, int kind, void *host_out, size_t bytes);
 int sgl_readback_wait(void);
 int sgl_texture_level_size(int handle, int level, int *w_out, int *h_out);
@@ -191,7 +192,14 @@ int sgl_peer_free(void *ptr);
 int sgl_peer_open(const uint8_t ipc_handle[64], void **ptr_out);
 int sgl_peer_close(void *ptr);
 int sgl_peer_signal(void *flag_device_ptr, uint32_t value);
+int sgl_peer_signal_after_copies(void *flag_device_ptr, uint32_t value);   /* same, on the copy stream: after all queued
+                                                                             sgl_texture_readback_async copies (whose destination
+                                                                             may be a peer mapping: copy-engine gather) */
 int sgl_peer_wait(const void *flags_device_ptr, int count, uint32_t value, int timeout_ms);
+/* rank 0's per-frame bookkeeping in one launch: wait until `count` done-flags (64-byte stride) are >= value, then store
+ * value into consumed_flags[1..count) (device pointers, usually peer mappings; entry 0 is ignored).  side_stream != 0
+ * queues it on an internal stream of its own, so that rank 0's rendering is not serialised behind the other ranks. */
+int sgl_peer_collect(const void *done_flags, int count, uint32_t value, void *const *consumed_flags, int timeout_ms, int side_stream);
 int sgl_peer_timeouts(uint64_t *count_out);                /* number of waits that gave up (must stay 0) */
 
 /* ---- unit-level entry points used by the known-answer tests (each wraps the device function the pipeline uses) */

@@ -56,7 +56,8 @@ C_ABI_SYMBOLS = [
     "sgl_texture_gen_mips", "sgl_texture_readback", "sgl_texture_readback_async", "sgl_readback_wait", "sgl_texture_level_size", "sgl_texture_device_ptr",
     "sgl_pass_begin", "sgl_set_viewport", "sgl_draw", "sgl_pass_end", "sgl_set_tile_owner_map", "sgl_tile_size",
     "sgl_set_rank", "sgl_tiles_owned", "sgl_tiles_pack", "sgl_tiles_unpack", "sgl_texture_set_mirror", "sgl_peer_alloc",
-    "sgl_peer_free", "sgl_peer_open", "sgl_peer_close", "sgl_peer_signal", "sgl_peer_wait", "sgl_peer_timeouts",
+    "sgl_peer_free", "sgl_peer_open", "sgl_peer_close", "sgl_peer_signal", "sgl_peer_signal_after_copies", "sgl_peer_wait", "sgl_peer_collect",
+    "sgl_peer_timeouts",
     "sgl_kat_barycentric", "sgl_kat_sample", "sgl_kat_blend", "sgl_kat_depth"]
 
 _lib = None
@@ -100,6 +101,8 @@ def load():
     _lib.sgl_peer_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     _lib.sgl_peer_close.argtypes = [C.c_void_p]
     _lib.sgl_peer_signal.argtypes = [C.c_void_p, C.c_uint32]
+    _lib.sgl_peer_signal_after_copies.argtypes = [C.c_void_p, C.c_uint32]
+    _lib.sgl_peer_collect.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_int, C.c_int]
     _lib.sgl_peer_wait.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int]
     _lib.sgl_peer_timeouts.argtypes = [C.POINTER(C.c_uint64)]
     _lib.sgl_texture_device_ptr.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]

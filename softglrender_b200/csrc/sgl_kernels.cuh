@@ -474,6 +474,35 @@ __global__ void sglPeerWaitKernel(const uint32_t *flags, int count, uint32_t val
   }
 }
 
+// Rank 0's side of the direct-store gather in ONE launch: wait until `count` done-flags reach `value`, then publish
+// `value` into every peer's consumed-flag (peers[0] = rank 0 itself is skipped).
+struct SglPeerPtrs {
+  uint32_t *p[64];
+};
+__global__ void sglPeerCollectKernel(const uint32_t *flags, int count, uint32_t value, SglPeerPtrs peers, long long timeoutCycles,
+                                     unsigned long long *counters) {
+  const int i = threadIdx.x;
+  if (i < count) {
+    const uint32_t *f = flags + (size_t) i * 16;
+    const long long t0 = clock64();
+    while (true) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if ((int32_t) (v - value) >= 0) break;
+      if (clock64() - t0 > timeoutCycles) {
+        atomicAdd(counters + 6, 1ull);
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  if (i >= 1 && i < count && peers.p[i]) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.p[i]), "r"(value) : "memory");
+  }
+}
+
 __global__ void sglFill32Kernel(uint32_t *dst, uint32_t value, size_t n) {
   size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t) gridDim.x * blockDim.x;

@@ -88,6 +88,7 @@ struct Ctx {
   // depth-only passes (shadow maps) run their pixel stage on an auxiliary stream: they start when all earlier pixel work
   // is done and only the next kernel that SAMPLES textures (or touches their depth texture) waits for them, so the
   // shadow pass of a frame overlaps the visibility kernel of its main pass
+  cudaStream_t peerStream = nullptr;   // rank 0's gather bookkeeping (sgl_peer_collect), decoupled from its own rendering
   cudaStream_t auxStream = nullptr;
   cudaEvent_t auxReady = nullptr, auxDone = nullptr;
   bool auxPending = false;
@@ -191,6 +192,7 @@ int syncAll() {
   CU(cudaStreamSynchronize(g.stream));
   for (cudaStream_t gs : g.geomStreams) if (gs) CU(cudaStreamSynchronize(gs));
   if (g.auxStream) CU(cudaStreamSynchronize(g.auxStream));
+  if (g.peerStream) CU(cudaStreamSynchronize(g.peerStream));
   g.auxPending = false;
   return SGL_OK;
 }
@@ -347,6 +349,7 @@ int sgl_init(int device_ordinal, int rank, int world) {
   CU(cudaEventCreateWithFlags(&g.auxReady, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&g.auxDone, cudaEventDisableTiming));
   CU(cudaStreamCreateWithFlags(&g.copyStream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&g.peerStream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&g.copyReady, cudaEventDisableTiming));
   {  // texture table entry 0 = 1x1 RGBA8 dummy: what unbound maps read in the straight-line shader paths
     CU(cudaMalloc(&g.dummyTexels, 256));
@@ -398,6 +401,7 @@ int sgl_shutdown(void) {
   }
   for (cudaStream_t gs : g.geomStreams) if (gs) cudaStreamDestroy(gs);
   if (g.auxStream) { cudaStreamSynchronize(g.auxStream); cudaStreamDestroy(g.auxStream); }
+  if (g.peerStream) { cudaStreamSynchronize(g.peerStream); cudaStreamDestroy(g.peerStream); }
   if (g.auxReady) cudaEventDestroy(g.auxReady);
   if (g.auxDone) cudaEventDestroy(g.auxDone);
   if (g.vis) cudaFree(g.vis);
@@ -749,10 +753,14 @@ int sgl_texture_readback_async(int handle, int layer, int level, int kind, void 
   if (!t->rbDone) CU(cudaEventCreateWithFlags(&t->rbDone, cudaEventDisableTiming));
   CU(cudaEventRecord(g.copyReady, g.stream));
   CU(cudaStreamWaitEvent(g.copyStream, g.copyReady, 0));
-  CU(cudaMemcpyAsync(host_out, src, need, cudaMemcpyDeviceToHost, g.copyStream));
+  // cudaMemcpyDefault: the destination may also be device memory -- another GPU's frame store mapped with sgl_peer_open
+  // (copy-engine form of the multi-GPU gather)
+  CU(cudaMemcpyAsync(host_out, src, need, cudaMemcpyDefault, g.copyStream));
   CU(cudaEventRecord(t->rbDone, g.copyStream));
   t->rbPending = true;
-  g.hostD2H += need;
+  cudaPointerAttributes pa;
+  if (cudaPointerGetAttributes(&pa, host_out) != cudaSuccess || pa.type != cudaMemoryTypeDevice) g.hostD2H += need;
+  cudaGetLastError();   // unregistered host memory reports an error on old drivers: not ours to keep
   return SGL_OK;
 }
 
@@ -1401,6 +1409,27 @@ int sgl_peer_close(void *ptr) {
 int sgl_peer_signal(void *flag_device_ptr, uint32_t value) {
   NEED_CTX();
   return launch("sglPeerSignalKernel", sglPeerSignalKernel, dim3(1), dim3(1), (uint32_t *) flag_device_ptr, value);
+}
+
+int sgl_peer_signal_after_copies(void *flag_device_ptr, uint32_t value) {
+  NEED_CTX();
+  gCur = g.copyStream;   // ordered behind every sgl_texture_readback_async queued so far
+  int rc = launch("sglPeerSignalKernel", sglPeerSignalKernel, dim3(1), dim3(1), (uint32_t *) flag_device_ptr, value);
+  gCur = nullptr;
+  return rc;
+}
+
+int sgl_peer_collect(const void *done_flags, int count, uint32_t value, void *const *consumed_flags, int timeout_ms, int side_stream) {
+  NEED_CTX();
+  if (count < 1 || count > 64) return fail(SGL_ERR_INVALID, "peer collect over %d ranks", count);
+  SglPeerPtrs pp;
+  memset(&pp, 0, sizeof(pp));
+  for (int i = 0; i < count; i++) pp.p[i] = consumed_flags ? (uint32_t *) consumed_flags[i] : nullptr;
+  long long cycles = (long long) std::max(timeout_ms, 1) * 2000000LL;
+  gCur = side_stream ? g.peerStream : g.stream;
+  int rc = launch("sglPeerCollectKernel", sglPeerCollectKernel, dim3(1), dim3(64), (const uint32_t *) done_flags, count, value, pp, cycles, g.dCounters);
+  gCur = nullptr;
+  return rc;
 }
 
 int sgl_peer_wait(const void *flags_device_ptr, int count, uint32_t value, int timeout_ms) {

@@ -175,7 +175,8 @@ class PeerFrameStore:
     """
     FLAG_STRIDE = 64
 
-    def __init__(self, lib, width, height, rank, world, frames_per_slot, slots=2, control_group=None, timeout_ms=2000, lag=0):
+    def __init__(self, lib, width, height, rank, world, frames_per_slot, slots=2, control_group=None, timeout_ms=2000, lag=0,
+                 dma=False):
         import torch
         import torch.distributed as dist
         from . import capi
@@ -184,6 +185,12 @@ class PeerFrameStore:
         # instead of pacing all of them on the slowest one each frame (0 <= lag <= slots - 1; flush() drains the tail)
         self.lag = max(0, min(lag, slots - 1))
         self.collected = 0
+        # dma=True: instead of mirrored stores from the shading kernel, the finished (resolved) frame is pushed into the
+        # slot by the copy engine (sgl_texture_readback_async onto the peer mapping) -- large NVLink packets, no SM work;
+        # only for whole frames (frame/view parallel), a tile-sharded frame has no contiguous owned region
+        self.dma = dma
+        self.texture, self.kind = None, 1
+        self._peer_array = None
         self.frame_bytes = width * height * 4
         self.header = self.FLAG_STRIDE * max(world, 1)
         store_bytes = self.header + self.frame_bytes * frames_per_slot * slots
@@ -238,27 +245,42 @@ class PeerFrameStore:
         f = self.frame_no
         if self.rank != 0 and f >= self.slots:
             capi.check(self.lib.sgl_peer_wait(self.local_flag.value, 1, f - self.slots + 1, self.timeout_ms))
-        capi.check(self.lib.sgl_texture_set_mirror(texture, self.slot_ptr(f, index)))
+        if self.dma:
+            if texture != self.texture:      # resolved colour of a multisample target, else the colour image itself
+                ptr, sz = C.c_void_p(), C.c_size_t()
+                self.kind = 1 if self.lib.sgl_texture_device_ptr(texture, 0, 0, 1, C.byref(ptr), C.byref(sz)) == 0 else 0
+            self.texture, self.index = texture, index
+        else:
+            capi.check(self.lib.sgl_texture_set_mirror(texture, self.slot_ptr(f, index)))
 
     def end_frame(self, consume=None):
         """Queue this rank's done-signal; on rank 0 also the wait for every rank, ``consume(ptr_of_slot)`` and the
         consumed-signals."""
         from . import capi
         f = self.frame_no
-        capi.check(self.lib.sgl_peer_signal(self.store.value + self.FLAG_STRIDE * self.rank, f + 1))
+        if self.dma:
+            capi.check(self.lib.sgl_texture_readback_async(self.texture, 0, 0, self.kind, self.slot_ptr(f, self.index), self.frame_bytes))
+            capi.check(self.lib.sgl_peer_signal_after_copies(self.store.value + self.FLAG_STRIDE * self.rank, f + 1))
+        else:
+            capi.check(self.lib.sgl_peer_signal(self.store.value + self.FLAG_STRIDE * self.rank, f + 1))
         self.frame_no = f + 1
         if self.rank == 0 and f - self.lag >= self.collected:
             self._collect(f - self.lag, consume)
 
     def _collect(self, upto, consume):
         from . import capi
+        if self._peer_array is None:
+            self._peer_array = (C.c_void_p * self.world)(*[C.c_void_p(p) for p in self.peer_flags])
         while self.collected <= upto:
             c = self.collected
-            capi.check(self.lib.sgl_peer_wait(self.store.value, self.world, c + 1, self.timeout_ms))
-            if consume is not None:
+            if consume is None:
+                # nothing to do with the frame on this stream: wait + consumed-signals in ONE kernel on the library's
+                # side stream, so rank 0's own rendering is never serialised behind the slowest peer
+                capi.check(self.lib.sgl_peer_collect(self.store.value, self.world, c + 1, self._peer_array, self.timeout_ms, 1))
+            else:
+                capi.check(self.lib.sgl_peer_wait(self.store.value, self.world, c + 1, self.timeout_ms))
                 consume(self.slot_ptr(c, 0))
-            for r in range(1, self.world):
-                capi.check(self.lib.sgl_peer_signal(self.peer_flags[r], c + 1))
+                capi.check(self.lib.sgl_peer_collect(self.store.value, self.world, c + 1, self._peer_array, self.timeout_ms, 0))
             self.collected = c + 1
 
     def flush(self, consume=None):

@@ -109,6 +109,26 @@ def main():
                     assert np.array_equal(a[r], full), "%s: frame-parallel store, slot %d differs" % (name, r)
             report["%s.p2p.frames" % name] = "byte-exact x%d ranks" % world
         capi.check(lib.sgl_texture_set_mirror(tex, None))
+
+        # (d) frame-parallel, copy-engine pushes instead of mirrored stores
+        store3 = M.PeerFrameStore(lib, w, h, rank, world, frames_per_slot=world, slots=4, control_group=ctl, lag=2, dma=True)
+        got3 = []
+        for f in range(6):
+            store3.begin_frame(tex, rank)
+            p.frame(sync=False)
+            store3.end_frame((lambda ptr: got3.append(M.device_view(ptr, world * w * h * 4).clone())) if rank == 0 else None)
+        store3.flush((lambda ptr: got3.append(M.device_view(ptr, world * w * h * 4).clone())) if rank == 0 else None)
+        capi.check(lib.sgl_wait_idle())
+        torch.cuda.synchronize()
+        dist.barrier()
+        assert store3.timeouts() == 0
+        if rank == 0:
+            assert len(got3) == 6
+            for t in got3:
+                a = t.cpu().numpy().reshape(world, h, w, 4)
+                for r in range(world):
+                    assert np.array_equal(a[r], full), "%s: copy-engine gather, slot %d differs" % (name, r)
+            report["%s.dma.frames" % name] = "byte-exact x%d ranks" % world
         p.close()
     dist.barrier()
     if rank == 0:
