@@ -136,8 +136,8 @@ def main():
     out = _json_only_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mgpu", default="frames", choices=["frames", "tiles"],
@@ -279,7 +279,20 @@ def main():
         if world > 1:
             dist.barrier()
 
+    # warm-up: W steps as asked, and in any case ~0.5 s of frames (clock ramp of an idle GPU, lazy module loading, first
+    # touch of the pinned buffers) -- all untimed.  The extra count is agreed on by all ranks BEFORE it runs (the peer
+    # frame store counts frames, so every rank must submit the same number).
+    t_warm = time.perf_counter()
     for _ in range(W):
+        step(False)
+    capi.check(lib.sgl_wait_idle())
+    per_step = max((time.perf_counter() - t_warm) / W, 1e-5)
+    n_extra = min(int(0.5 / per_step) + 1, 20000)
+    if world > 1:
+        t = torch.tensor([n_extra], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n_extra = int(t.item())
+    for _ in range(n_extra):
         step(False)
     flush_store(False)
     sync_all()
