@@ -220,7 +220,7 @@ def main():
         if gather in ("p2p", "dma"):
             try:
                 store = M.PeerFrameStore(lib, WIDTH, HEIGHT, rank, world, frames_per_slot=1 if tiles else world, slots=4,
-                                         control_group=ctl, lag=2, dma=(gather == "dma"))
+                                         control_group=ctl, lag=2, dma=(gather == "dma"), timeout_ms=10000)
             except RuntimeError as e:      # CUDA IPC not permitted on this box (all ranks agree): NCCL moves the same bytes
                 gather = "nccl (p2p unavailable: %s)" % str(e)[:80]
         if store is None and not tiles:

@@ -92,7 +92,7 @@ struct Ctx {
   cudaStream_t auxStream = nullptr;
   cudaEvent_t auxReady = nullptr, auxDone = nullptr;
   bool auxPending = false;
-  int auxDepthTex = 0;
+  std::vector<int> auxDepthTex;   // depth textures written by the auxiliary-stream passes not joined yet
   int noOverlap = 0;           // SGL_NO_OVERLAP=1: geometry and pixel stages on one stream (A/B runs)
   int noPassSplit = 0;         // SGL_NO_PASS_SPLIT=1: a pass with a blended tail runs entirely in the fused kernel (A/B runs)
   int noSplit = 0;             // SGL_NO_SPLIT=1: heavy MSAA tiles are not split into quarter-tile CTAs (A/B runs)
@@ -148,6 +148,7 @@ void joinAux() {
   if (!g.auxPending) return;
   cudaStreamWaitEvent(g.stream, g.auxDone, 0);
   g.auxPending = false;
+  g.auxDepthTex.clear();
 }
 
 size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -194,6 +195,7 @@ int syncAll() {
   if (g.auxStream) CU(cudaStreamSynchronize(g.auxStream));
   if (g.peerStream) CU(cudaStreamSynchronize(g.peerStream));
   g.auxPending = false;
+  g.auxDepthTex.clear();
   return SGL_OK;
 }
 
@@ -648,6 +650,10 @@ int sgl_texture_upload(int handle, int layer, int level, const void *host_data) 
   TextureRec *t = tex(handle);
   if (!t || layer < 0 || layer >= t->obj.layers || level < 0 || level >= t->obj.levels) return fail(SGL_ERR_INVALID, "bad texture upload target");
   if (t->obj.samples != 1) return fail(SGL_ERR_INVALID, "setImageData not supported on multisample textures");   // TextureSoft.h:115-118
+  if (t->rbPending) {   // an asynchronous read-back still reads the old contents
+    CU(cudaStreamWaitEvent(g.stream, t->rbDone, 0));
+    t->rbPending = false;
+  }
   int w = sglLevelDim(t->obj.width, level), h = sglLevelDim(t->obj.height, level);
   size_t bytes = (size_t) w * h * 4;
   uint8_t *dst = levelPtr(*t, layer, level);
@@ -1100,7 +1106,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
       CU(cudaEventRecord(g.auxDone, g.auxStream));
       CU(cudaEventRecord(arena.pixelDone, g.auxStream));
       g.auxPending = true;
-      g.auxDepthTex = g.depthTex;
+      g.auxDepthTex.push_back(g.depthTex);
       arena.used = true;
       g.hostDraws += nDraws;
       return SGL_OK;
@@ -1136,7 +1142,8 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   }
   rc = toPixelStage();
   if (rc) return rc;
-  if (g.auxPending && (g.depthTex == g.auxDepthTex || !overlap)) joinAux();   // this pass writes that depth texture
+  if (g.auxPending && (!overlap || std::find(g.auxDepthTex.begin(), g.auxDepthTex.end(), g.depthTex) != g.auxDepthTex.end()))
+    joinAux();   // this pass writes a depth texture an auxiliary-stream pass is still producing
   // Deferred (visibility + shading) path for passes made of opaque draws whose point/line programs have no varyings;
   // everything else (blending, wireframe with a lit program) takes the fused tile kernel.
   bool deferred = !g.forceFused;
