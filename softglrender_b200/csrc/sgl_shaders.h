@@ -181,6 +181,31 @@ SGL_HD float sglShadowCalc(const SglFsCtx &c, V4 fragPos, V3 normal, V3 lightDir
   V2 po = v2(1.0f / (float) sm.tex->width, 1.0f / (float) sm.tex->height);
   bool rev = uI(*c.draw, 0) != 0;
   float shadow = 0.0f;
+  if (sm.filter == SGL_FILTER_NEAREST && sm.tex->format == SGL_FMT_FLOAT32 && sm.tex->layout == SGL_LAYOUT_LINEAR &&
+      sm.tex->samples == 1 && sm.tex->base != nullptr) {
+    // the shadow map as the Viewer binds it (NEAREST float texture): same nine sampleNearest taps, with the level view
+    // resolved once and all nine texel loads in flight before the first comparison
+    const int w = sm.tex->width, h = sm.tex->height;
+    const uint32_t *base = (const uint32_t *) (sm.tex->base + sm.tex->levelOffset[0]);
+    uint32_t tap[9];
+    int k = 0;
+    for (int x = -1; x <= 1; ++x) {
+      for (int y = -1; y <= 1; ++y, ++k) {
+        int ix = (int) floorf(xmul(proj.x + (float) x * po.x, (float) w));
+        int iy = (int) floorf(xmul(proj.y + (float) y * po.y, (float) h));
+        const int rx = sglWrapAxis(ix, w, sm.wrap), ry = sglWrapAxis(iy, h, sm.wrap);
+        const bool border = rx == 1 || ry == 1, oob = (rx | ry) != 0;
+        const uint32_t t = SGL_LDG(base + (border || oob ? 0 : (uint32_t) iy * (uint32_t) w + (uint32_t) ix));
+        tap[k] = border ? sm.border : (oob ? 0u : t);
+      }
+    }
+    for (k = 0; k < 9; k++) {
+      const float pcf = sglBitsFloat(tap[k]);
+      if (rev) shadow += (cur + bias < pcf) ? 1.0f : 0.0f;
+      else shadow += (cur - bias > pcf) ? 1.0f : 0.0f;
+    }
+    return shadow / 9.0f;
+  }
   for (int x = -1; x <= 1; ++x) {
     for (int y = -1; y <= 1; ++y) {
       float pcf = sglTexture2DFloat(sm, v2(proj.x + (float) x * po.x, proj.y + (float) y * po.y));
