@@ -199,6 +199,28 @@ SGL_HD bool sglTriSurelyOutside(const SglTriEdge &e, float cx, float cy, float h
   return false;
 }
 
+// Mirror image of sglTriSurelyOutside: true only if barycentric() is CERTAIN to report "inside" (b0, b1, b2 all > 0)
+// for every sample position inside the rectangle (cx +- hx, cy +- hy); same error model, same 2^-20 guard.
+SGL_HD bool sglTriSurelyInside(const SglTriEdge &e, float cx, float cy, float hx, float hy) {
+  const float K = 9.5367431640625e-7f;   // 2^-20
+  float azc = e.x0 - cx, bzc = e.y0 - cy;
+  float sux = e.say * bzc - azc * e.sby;
+  float suy = azc * e.sbx - e.sax * bzc;
+  float aaz = fabsf(azc) + hx + 1.f, abz = fabsf(bzc) + hy + 1.f;
+  float err = K * (e.tA * abz + e.tB * aaz);
+  float rux = hx * fabsf(e.by) + hy * fabsf(e.ay);
+  float ruy = hx * fabsf(e.bx) + hy * fabsf(e.ax);
+  return sux > rux + err && suy > ruy + err && (sux + suy) - e.auz < -(rux + ruy + 2.f * err + K * e.auz);
+}
+
+// All three vertex depths are exactly +0 (a skybox under reversed-Z, SkyboxSoft.h:67-76).  Then the interpolated depth of
+// every INSIDE sample is exactly +0 as well: z = (b0*0 + b1*0) + (b2*0 + 0*0) with finite b >= 0; b0 = 1 - (b1 + b2) is
+// never -0, so the first pair is +0, the second pair ends in + (+0), and (+0) + (+0) = +0.  For pixels that are surely
+// inside, coverage and depth are therefore known without evaluating barycentric() at all.
+SGL_HD bool sglTriFlatZeroDepth(const SglPrim &p) {
+  return (sglFloatBits(p.v[0][2]) | sglFloatBits(p.v[1][2]) | sglFloatBits(p.v[2][2])) == 0u;
+}
+
 // RendererSoft::barycentric (RendererSoft.cpp:1021-1056) in the oracle binary's association:
 //   a = (x2-x0, x1-x0, x0-px) ; b = (y2-y0, y1-y0, y0-py)
 //   u = fma(a.yzx, b.zxy, -rn(a.zxy * b.yzx)) ; u /= u.z ; bc = (1 - (u.x + u.y), u.y, u.x)
@@ -243,6 +265,21 @@ SGL_HD uint32_t sglCoverTriangle(const SglPrim &p, const SglTriEdge &e, int px, 
   float fx = (float) px, fy = (float) py;
   // all sample positions (and the centre) lie within +-0.375 of the pixel centre
   if (sglTriSurelyOutside(e, fx + 0.5f, fy + 0.5f, NS > 1 ? 0.375f : 0.f, NS > 1 ? 0.375f : 0.f)) return 0;
+  if (NS > 1 && sglTriFlatZeroDepth(p) && sglTriSurelyInside(e, fx + 0.5f, fy + 0.5f, 0.375f, 0.375f)) {
+    // every sample and the centre are covered, depth is +0 at each of them (see sglTriFlatZeroDepth)
+    shadeIdx = 4;
+    const uint32_t fl = p.flags;
+    const bool dt = (fl & SGL_PF_DEPTH_TEST) != 0;
+    const int fn = (fl >> SGL_PF_DEPTH_FUNC_SHIFT) & 7;
+    uint32_t pass = 0;
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+      if (dt && (!hasDepth || !sglDepthTest(0.f, depth[s], fn))) continue;
+      zOut[s] = 0.f;
+      pass |= 1u << s;
+    }
+    return pass;
+  }
   uint32_t geo = 0;
   float bc[NS][3];
 #pragma unroll

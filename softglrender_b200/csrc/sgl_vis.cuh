@@ -208,16 +208,23 @@ __device__ __forceinline__ void sglVisSamplePrim(const SglPassParams &P, const S
     if (cand && sglTriSurelyOutside(vp.e, fx + 0.5f, fy + 0.5f, 0.375f, 0.375f)) cand = false;
     float b0 = 0.f, b1 = 0.f, b2 = 0.f;
     bool in = false;
-    if (cand) {
+    // flat +0 depth and surely inside: all four samples and the centre covered, z == +0 (sglTriFlatZeroDepth)
+    const bool flat = cand && sglTriFlatZeroDepth(p) && sglTriSurelyInside(vp.e, fx + 0.5f, fy + 0.5f, 0.375f, 0.375f);
+    if (flat) in = true;
+    else if (cand) {
       float ox, oy;
       sglSampleOffset(4, s, ox, oy);
       in = sglBarycentric(vp.e, xadd(ox, fx), xadd(oy, fy), b0, b1, b2);
     }
     const uint32_t g4 = (__ballot_sync(0xffffffffu, in) >> (lane & 28)) & 0xFu;   // geometric coverage of this pixel
     if (g4 == 0 || !in) return;
-    float c0, c1, c2;
-    const int shadeIdx = sglBarycentric(vp.e, xadd(fx, 0.5f), xadd(fy, 0.5f), c0, c1, c2) ? 4 : (__ffs(g4) - 1);
-    float z = sglInterpZ(p, 2, b0, b1, b2);
+    int shadeIdx = 4;
+    float z = 0.f;
+    if (!flat) {
+      float c0, c1, c2;
+      shadeIdx = sglBarycentric(vp.e, xadd(fx, 0.5f), xadd(fy, 0.5f), c0, c1, c2) ? 4 : (__ffs(g4) - 1);
+      z = sglInterpZ(p, 2, b0, b1, b2);
+    }
     if (z < 0.f || z > 1.f) return;                    // depth-range clipping (multisample path)
     z = gclamp(z, 0.f, 1.f);
     if (flags & SGL_PF_DEPTH_TEST) {
