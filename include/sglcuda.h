@@ -94,6 +94,8 @@ typedef struct SglDraw {
   SglSamplerBinding samplers[SGL_MAX_SAMPLER_SLOTS];   /* slot order = sgl_shader_sampler_slot */
 } SglDraw;
 
+/* Geometry is never dropped silently: if the clip-vertex arena of a pass was too small, the next synchronising call
+ * (sgl_wait_idle, any read-back, sgl_get_counters) returns SGL_ERR_OVERFLOW once, and later passes get a larger arena. */
 typedef struct SglCounters {
   uint64_t passes, draws, primitives_in, primitives_binned, fragments_shaded, samples_written;
   uint64_t kernel_launches;   /* launches of kernels defined in this library */
@@ -102,6 +104,7 @@ typedef struct SglCounters {
   uint64_t d2h_bytes;         /* device->host bytes copied by read-backs */
   uint64_t host_ns_pass_end;  /* CPU time spent inside sgl_pass_end (arena layout, uploads, launches) */
   uint64_t host_ns_draw;      /* CPU time spent inside sgl_draw (state snapshot) */
+  uint64_t bin_spills;        /* primitives that went to the pass-wide list because the tile bins were full (correct, slower) */
 } SglCounters;
 
 /* ---- context ---------------------------------------------------------------------------------------- */
@@ -129,6 +132,9 @@ int sgl_get_tile_list_sizes(uint32_t *out, int capacity, int *tiles_x_out, int *
 /* enable != 0: the visibility kernel of later colour passes records per-tile start/end times (globaltimer ns);
  * out (may be NULL) receives [tiles][2] of the most recent such pass */
 int sgl_debug_tile_times(int enable, unsigned long long *out, int capacity_tiles);
+/* testing aid: cap the tile-bin region (entries) and the minimum clip arenas (vertices, fan triangles) of later passes so
+ * that the bin-spill and clip-overflow paths can be exercised with small inputs; 0 restores a default */
+int sgl_debug_set_limits(long long bin_capacity, long long clip_min_vertices, long long clip_min_fans);
 int sgl_set_profiling(int on);
 int sgl_get_kernel_times(SglKernelTime *out, int capacity);   /* returns the number of entries written */
 
@@ -150,7 +156,9 @@ int sgl_texture_destroy(int handle);
 /* host data is row-major w x h of the level, 4 bytes per texel; converted to the texture's layout */
 int sgl_texture_upload(int handle, int layer, int level, const void *host_data);
 int sgl_texture_gen_mips(int handle);                                   /* SamplerSoft.h:90-110,241-252 */
-/* kind 0: attachment (w*h*samples*4 bytes, [y][x][sample]); kind 1: resolved colour of an MS texture */
+/* kind 0: attachment (w*h*samples*4 bytes, [y][x][sample]); kind 1: resolved colour of an MS texture; kind 2: the level's
+ * raw storage in the texture's own layout, padded to whole tiles exactly like TiledBuffer / MortonBuffer
+ * (Base/Buffer.h:143-158,174-202; size = sgl_texture_device_ptr's bytes_out) */
 int sgl_texture_readback(int handle, int layer, int level, int kind, void *host_out, size_t bytes);
 /* pipelined form: queued behind all submitted work on a second stream; a later pass that overwrites the image waits for
  * the copy on the device, the host waits with sgl_readback_wait() (or sgl_wait_idle()).  host_out should be pinned host
@@ -207,9 +215,12 @@ int sgl_peer_timeouts(uint64_t *count_out);                /* number of waits th
  * for one triangle (3 x float4 screen positions) over n sample positions; out: bc[3], inside flag, z, 1/w per sample */
 int sgl_kat_barycentric(const float *tri_xyzw, const float *sample_xy, int n, float *bc_out, int *inside_out,
                         float *zw_out);
-/* BaseSampler::textureImpl (SamplerSoft.h:118-168) on a bound texture for n coordinates (2D: uv, cube: xyz) */
+/* BaseSampler::textureImpl (SamplerSoft.h:118-168) on a bound texture for n coordinates (2D: uv, cube: xyz); lod and
+ * offsets_xy (2 ints per coordinate, texture2DLodOffset) may be NULL.  split_phase != 0 evaluates the split-phase bilinear
+ * taps the straight-line shader paths use for "simple" samplers (RGBA8, linear layout, LINEAR filter, REPEAT or
+ * CLAMP_TO_EDGE; SGL_ERR_INVALID otherwise) instead of the general function -- both must give the same bits. */
 int sgl_kat_sample(int texture, int filter_min, int wrap, int border, const float *coords, const float *lod,
-                   int n, uint32_t *rgba_or_float_bits_out);
+                   const int32_t *offsets_xy, int n, int split_phase, uint32_t *rgba_or_float_bits_out);
 /* calcBlendColor (BlendSoft.h:44-56) and DepthTest (DepthSoft.h:13-25) tables */
 int sgl_kat_blend(const SglRenderStates *states, const float *src_rgba, const float *dst_rgba, int n, float *out_rgba);
 int sgl_kat_depth(int func, const float *a, const float *b, int n, int *pass_out);

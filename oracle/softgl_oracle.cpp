@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <string>
 
@@ -80,10 +81,11 @@ uint32_t pixelWrapped(const Sampler &s, int layer, int level, int x, int y) {
   return t->levels[layer][level][(size_t) y * w + x];
 }
 
-// glm::mix on u8vec4 / float as compiled: fma(y, a, x * (1 - a)), u8 conversion truncates
+// glm::mix as compiled (objdump of samplePixelBilinear<RGBA> / <float> in the reference binary):
+//   u8vec4: fma(y, a, x * (1 - a)), u8 conversion truncates;   float: fma(x, 1 - a, y * a)
 uint32_t mixTexel(int format, uint32_t a, uint32_t b, float f) {
   float omf = 1.0f - f;
-  if (format == TextureFormat_FLOAT32) return floatToBits(fmaf(bitsToFloat(b), f, bitsToFloat(a) * omf));
+  if (format == TextureFormat_FLOAT32) return floatToBits(fmaf(bitsToFloat(a), omf, bitsToFloat(b) * f));
   uint32_t r = 0;
   for (int c = 0; c < 4; c++) {
     float x = (float) ((a >> (8 * c)) & 255u), y = (float) ((b >> (8 * c)) & 255u);
@@ -620,6 +622,17 @@ bool depthTestFn(float a, float b, int fn) {
   return a < b;
 }
 
+// barycentric (RendererSoft.cpp:1021-1056), SIMD association
+bool barycentricO(const f4 *v, float px, float py, float *bc) {
+  float ax = v[2].x - v[0].x, ay = v[1].x - v[0].x, az = v[0].x - px;
+  float bx = v[2].y - v[0].y, by = v[1].y - v[0].y, bz = v[0].y - py;
+  float ux = fmaf(ay, bz, -(az * by)), uy = fmaf(az, bx, -(ax * bz)), uz = fmaf(ax, by, -(ay * bx));
+  if (std::fabs(uz) < FLT_EPSILON) return false;
+  ux = ux / uz; uy = uy / uz;
+  bc[0] = 1.f - (ux + uy); bc[1] = uy; bc[2] = ux;
+  return !(bc[0] < 0 || bc[1] < 0 || bc[2] < 0);
+}
+
 class RendererOracle : public Renderer {
  public:
   RendererType type() override { return Renderer_SOFT; }
@@ -899,15 +912,7 @@ class RendererOracle : public Renderer {
   struct SampleO { bool inside; int fx, fy; float x, y, z, w; float bc[3]; };
   struct PixelO { bool inside; SampleO s[5]; int shade; int count; int coverage; float vary[32]; };
 
-  bool barycentric(const f4 *v, float px, float py, float *bc) {   // barycentric (:1021-1056), SIMD association
-    float ax = v[2].x - v[0].x, ay = v[1].x - v[0].x, az = v[0].x - px;
-    float bx = v[2].y - v[0].y, by = v[1].y - v[0].y, bz = v[0].y - py;
-    float ux = fmaf(ay, bz, -(az * by)), uy = fmaf(az, bx, -(ax * bz)), uz = fmaf(ax, by, -(ay * bx));
-    if (std::fabs(uz) < FLT_EPSILON) return false;
-    ux = ux / uz; uy = uy / uz;
-    bc[0] = 1.f - (ux + uy); bc[1] = uy; bc[2] = ux;
-    return !(bc[0] < 0 || bc[1] < 0 || bc[2] < 0);
-  }
+  bool barycentric(const f4 *v, float px, float py, float *bc) { return barycentricO(v, px, py, bc); }
 
   void rasterTriangle(const PrimO &t) {
     const VertexO *vx[3] = {&verts_[t.i[0]], &verts_[t.i[1]], &verts_[t.i[2]]};
@@ -1096,6 +1101,95 @@ bool oracleLoadShaders(ShaderProgram &program, int shading) {   // ShaderProgram
     for (int i = 0; i < 8 && m->defines[i]; i++)
       if (d == m->defines[i]) p->defines |= 1u << i;
   return true;
+}
+
+
+// ---- unit-level known-answer entry points (same file protocol as oracle/ref_kat.cpp, so that the restatement can be
+//      checked against the vectors the reference produced: tests/golden/unit_kats.npz)
+static std::vector<uint8_t> katReadFile(const char *path) {
+  std::vector<uint8_t> v;
+  FILE *f = fopen(path, "rb");
+  if (!f) return v;
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  v.resize(n);
+  if (n && fread(v.data(), 1, n, f) != (size_t) n) v.clear();
+  fclose(f);
+  return v;
+}
+
+int oracleKatMain(int argc, char **argv) {
+  if (argc >= 4 && !strcmp(argv[1], "sample")) {
+    struct { int32_t w, h, layers, format, mips, filter, wrap, border, n, hasOffset; } H;
+    std::vector<uint8_t> blob = katReadFile(argv[2]);
+    if (blob.size() < sizeof(H)) return 2;
+    memcpy(&H, blob.data(), sizeof(H));
+    const uint8_t *p = blob.data() + sizeof(H);
+    TextureDesc d;
+    d.width = H.w; d.height = H.h; d.type = H.layers == 6 ? TextureType_CUBE : TextureType_2D;
+    d.format = (TextureFormat) H.format; d.useMipmaps = H.mips != 0; d.multiSample = false;
+    TextureOracle tex(d);
+    tex.allocate(d.useMipmaps);
+    const size_t texels = (size_t) H.w * H.h;
+    for (int l = 0; l < H.layers; l++) memcpy(tex.levels[l][0].data(), p + (size_t) l * texels * 4, texels * 4);
+    if (d.useMipmaps) tex.generateMipmaps();
+    p += texels * 4 * H.layers;
+    const int comps = H.layers == 6 ? 3 : 2;
+    const float *coords = (const float *) p, *lod = coords + (size_t) comps * H.n;
+    const int32_t *offs = (const int32_t *) (lod + H.n);
+    Sampler s;
+    s.tex = &tex; s.filter = H.filter; s.wrap = H.wrap;
+    float bf = H.border == Border_WHITE ? 1.f : 0.f;          // TextureSoft::getBorderColor (TextureSoft.h:158-164)
+    s.border = H.format == TextureFormat_FLOAT32 ? floatToBits(bf) : (H.border == Border_WHITE ? 0xFFFFFFFFu : 0u);
+    std::vector<uint32_t> out(H.n);
+    for (int i = 0; i < H.n; i++) {
+      if (H.layers == 6) {
+        int face; float u, v;
+        cubeFaceUV(coords[3 * i], coords[3 * i + 1], coords[3 * i + 2], face, u, v);
+        out[i] = textureImpl(s, face, u, v, lod[i]);
+      } else {
+        out[i] = textureImpl(s, 0, coords[2 * i], coords[2 * i + 1], lod[i], H.hasOffset ? offs[2 * i] : 0, H.hasOffset ? offs[2 * i + 1] : 0);
+      }
+    }
+    FILE *f = fopen(argv[3], "wb");
+    if (!f) return 2;
+    fwrite(out.data(), 4, out.size(), f);
+    fclose(f);
+    return 0;
+  }
+  if (argc >= 4 && !strcmp(argv[1], "bary")) {
+    std::vector<uint8_t> blob = katReadFile(argv[2]);
+    if (blob.size() < 8) return 2;
+    int32_t nTri, nPer;
+    memcpy(&nTri, blob.data(), 4);
+    memcpy(&nPer, blob.data() + 4, 4);
+    const float *p = (const float *) (blob.data() + 8);
+    FILE *f = fopen(argv[3], "wb");
+    if (!f) return 2;
+    for (int t = 0; t < nTri; t++) {
+      f4 v[3];
+      for (int k = 0; k < 3; k++) v[k] = {p[4 * k], p[4 * k + 1], p[4 * k + 2], p[4 * k + 3]};
+      p += 12;
+      for (int sidx = 0; sidx < nPer; sidx++, p += 2) {
+        float bc[3] = {0.f, 0.f, 0.f}, zw[2] = {0.f, 0.f};
+        bool in = barycentricO(v, p[0], p[1], bc);
+        if (in) {   // interpolateBarycentric(&position.z, vertZ, 2, bc) (RendererSoft.cpp:794,1110-1112)
+          float bz[4] = {bc[0], bc[1], bc[2], 0.f}, zs[4] = {v[0].z, v[1].z, v[2].z, 0.f}, ws[4] = {v[0].w, v[1].w, v[2].w, 0.f};
+          zw[0] = dpps(bz, zs);
+          zw[1] = dpps(bz, ws);
+        }
+        int32_t in32 = in ? 1 : 0;
+        fwrite(&in32, 4, 1, f);
+        fwrite(bc, 4, 3, f);
+        fwrite(zw, 4, 2, f);
+      }
+    }
+    fclose(f);
+    return 0;
+  }
+  fprintf(stderr, "usage: oracle_kat sample in out | bary in out\n");
+  return 1;
 }
 
 }  // namespace SoftGL

@@ -44,6 +44,7 @@ class TextureOracle : public Texture {
 
 std::shared_ptr<Renderer> createRendererOracle();
 bool oracleLoadShaders(ShaderProgram &program, int shading);
+int oracleKatMain(int argc, char **argv);   // unit-level KAT entry (same protocol as oracle/ref_kat.cpp)
 
 }  // namespace SoftGL
 

@@ -47,8 +47,11 @@ struct SglDepthAlloc {
     return idx < d.vertexCap ? idx : -1;
   }
   __device__ int newAppendSlots(const SglDrawRec &d, int) { return d.appendBase; }
-  __device__ void overflow() { atomicAdd(D.counters + 7, 1ull); }
-  __device__ void binPrim(int, const SglPrim &) {}
+  __device__ void overflow() {
+    atomicAdd(D.counters + 7, 1ull);
+    *(volatile unsigned int *) D.overflowHost = 1u;
+  }
+  __device__ bool binPrim(int, const SglPrim &) { return false; }
   __device__ void pushLarge(const SglPrim &p) {
     uint32_t q = atomicAdd(D.largeCount, 1u);
     if (q < D.largeCapacity) D.large[q] = p; else overflow();
@@ -67,7 +70,15 @@ struct SglDepthAlloc {
     rows = rows < 4 ? 4 : (rows & ~3);                      // bands are whole 8x4 steps
     const int bands = (h + rows - 1) / rows;
     uint32_t q = atomicAdd(D.queueCount, (uint32_t) bands);
-    if (q + bands > D.queueCapacity) { atomicSub(D.queueCount, (uint32_t) bands); pushLarge(p); return; }
+    if (q + bands > D.queueCapacity) {
+      // queue full: the triangle goes to the tile-parallel kernel.  The reservation is NOT rolled back (a roll-back races
+      // with concurrent reservations); the part of it that lies inside the queue is filled with empty records instead.
+      SglPrim none = p;
+      none.by0 = 1; none.by1 = 0;
+      for (uint32_t k = q; k < D.queueCapacity && k < q + (uint32_t) bands; k++) D.queue[k] = none;
+      pushLarge(p);
+      return;
+    }
     p.bx0 = (int16_t) x0; p.bx1 = (int16_t) x1;
     for (int b = 0; b < bands; b++) {
       p.by0 = (int16_t) (y0 + b * rows);

@@ -14,6 +14,7 @@ struct SglDepthPass {
   uint32_t *largeCount;
   uint32_t largeCapacity;
   unsigned long long *counters;
+  unsigned int *overflowHost;   // pinned host word, set when a triangle had to be dropped
   const uint8_t *tileOwner;
   int tilesX, rank;
 };

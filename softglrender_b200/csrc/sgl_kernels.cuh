@@ -20,7 +20,10 @@ struct SglSetupShared {
   uint32_t *bigList;
   uint32_t *bigCount;
   uint32_t bigCapacity;
+  uint32_t *binReserved;       // running upper bound of bin entries handed out (zero-initialised with the counters)
+  uint32_t binCapacity;
   unsigned long long *counters;
+  unsigned int *overflowHost;  // pinned host word: set when geometry had to be DROPPED (clip arena full) -- read at sync points
   int tilesX, tilesY, fbW, fbH;
   const uint8_t *tileOwner;
   int rank;
@@ -33,6 +36,33 @@ __device__ __forceinline__ bool sglPrimTiles(const SglPrim &p, int fbW, int fbH,
   if (x1 < x0 || y1 < y0) return false;
   tx0 = x0 / SGL_TILE; ty0 = y0 / SGL_TILE; tx1 = x1 / SGL_TILE; ty1 = y1 / SGL_TILE;
   return true;
+}
+
+// atomicAdd(counter, n) for the lanes that are converged here, as ONE atomic per warp (the reservation counter of the bins
+// is a single address: 10 M primitives would otherwise serialise on it)
+__device__ __forceinline__ uint32_t sglWarpAggregatedAdd(uint32_t *counter, uint32_t n) {
+  const uint32_t active = __activemask();
+  const int lane = threadIdx.x & 31, leader = __ffs(active) - 1;
+  uint32_t incl = n;
+  if (active == 0xffffffffu) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+  } else {   // partially converged warp: sum the active lanes at or below this one
+    incl = 0;
+    for (uint32_t m = active; m; m &= m - 1) {
+      const int src = __ffs(m) - 1;
+      const uint32_t v = __shfl_sync(active, n, src);
+      if (src <= lane) incl += v;
+    }
+  }
+  const uint32_t total = __shfl_sync(active, incl, 31 - __clz(active));
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, total);
+  base = __shfl_sync(active, base, leader);
+  return base + incl - n;
 }
 
 struct SglDeviceAlloc {
@@ -48,15 +78,26 @@ struct SglDeviceAlloc {
     int a = atomicAdd(d.appendCounter, n);
     return a + n <= d.appendCap ? d.appendBase + a : -1;
   }
-  __device__ void overflow() { atomicAdd(S.counters + 7, 1ull); }
-  __device__ void binPrim(int slot, const SglPrim &p) {
+  __device__ void overflow() {
+    atomicAdd(S.counters + 7, 1ull);
+    *(volatile unsigned int *) S.overflowHost = 1u;
+  }
+  // Counts the primitive into the bins of the tiles it can touch.  Returns true when it goes to the pass-wide big list
+  // instead (SGL_PF_BIG): more than SGL_BIG_PRIM_TILES tiles, or the bin region is exhausted -- the big list holds one
+  // entry per primitive slot at most, so binning can never drop geometry, it only gets slower.
+  __device__ bool binPrim(int slot, const SglPrim &p) {
     int tx0, ty0, tx1, ty1;
-    if (!sglPrimTiles(p, S.fbW, S.fbH, tx0, ty0, tx1, ty1)) return;
+    if (!sglPrimTiles(p, S.fbW, S.fbH, tx0, ty0, tx1, ty1)) return false;
     int n = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
-    if (n > SGL_BIG_PRIM_TILES) {
+    bool big = n > SGL_BIG_PRIM_TILES;
+    if (!big) {
+      const uint32_t r = sglWarpAggregatedAdd(S.binReserved, (uint32_t) n);
+      if (r + (uint32_t) n > S.binCapacity || r + (uint32_t) n < r) { big = true; atomicAdd(S.counters + 1, 1ull); }
+    }
+    if (big) {
       uint32_t b = atomicAdd(S.bigCount, 1u);
       if (b < S.bigCapacity) S.bigList[b] = (uint32_t) slot;
-      return;
+      return true;
     }
     for (int ty = ty0; ty <= ty1; ty++)
       for (int tx = tx0; tx <= tx1; tx++) {
@@ -65,6 +106,7 @@ struct SglDeviceAlloc {
         if (!sglPrimNearTile(p, tx, ty)) continue;
         atomicAdd(&S.tileCount[t], 1u);
       }
+    return false;
   }
 };
 
@@ -177,15 +219,14 @@ __global__ void __launch_bounds__(256) sglBinFillKernel(SglPassParams P) {
   if (!(p.flags & SGL_PF_VALID)) return;
   int tx0, ty0, tx1, ty1;
   if (!sglPrimTiles(p, P.fbW, P.fbH, tx0, ty0, tx1, ty1)) return;
-  int n = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
-  if (n > SGL_BIG_PRIM_TILES) return;   // lives in the pass-wide big list (bigCapacity >= primSlots, never overflows)
+  if (p.flags & SGL_PF_BIG) return;     // lives in the pass-wide big list (bigCapacity >= primSlots, never overflows)
   for (int ty = ty0; ty <= ty1; ty++)
     for (int tx = tx0; tx <= tx1; tx++) {
       int t = ty * P.tilesX + tx;
       if (P.tileOwner && P.tileOwner[t] != P.rank) continue;
       if (!sglPrimNearTile(p, tx, ty)) continue;
       uint32_t pos = P.tileOffset[t] + atomicAdd(&P.tileCursor[t], 1u);
-      if (pos < P.binCapacity) P.binSlots[pos] = (uint32_t) slot;
+      P.binSlots[pos] = (uint32_t) slot;   // pos < binCapacity: the setup kernel reserved every entry it counted
     }
 }
 
@@ -527,7 +568,7 @@ __global__ void sglKatBarycentricKernel(const float *tri, const float *xy, int n
 }
 
 __global__ void sglKatSampleKernel(const SglTexObj *textures, int tex, int filter, int wrap, uint32_t border, const float *coords,
-                                   const float *lod, int n, uint32_t *out) {
+                                   const float *lod, const int32_t *offs, int n, int splitPhase, uint32_t *out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   SglSampler s;
@@ -535,15 +576,14 @@ __global__ void sglKatSampleKernel(const SglTexObj *textures, int tex, int filte
   s.filter = filter;
   s.wrap = wrap;
   s.border = border;
-  float l = lod ? lod[i] : 0.f;
-  if (s.tex->layers == 6) {
-    int face;
-    float u, v;
-    sglCubeFace(coords[3 * i], coords[3 * i + 1], coords[3 * i + 2], face, u, v);
-    out[i] = sglTextureImpl(s, face, u, v, l, 0, 0);
-  } else {
-    out[i] = sglTextureImpl(s, 0, coords[2 * i], coords[2 * i + 1], l, 0, 0);
-  }
+  const float l = lod ? lod[i] : 0.f;
+  const int ox = offs ? offs[2 * i] : 0, oy = offs ? offs[2 * i + 1] : 0;
+  int face = 0;
+  float u, v;
+  if (s.tex->layers == 6) sglCubeFace(coords[3 * i], coords[3 * i + 1], coords[3 * i + 2], face, u, v);
+  else { u = coords[2 * i]; v = coords[2 * i + 1]; }
+  if (splitPhase) out[i] = sglTapMix(sglTapIssue(sglTapView(s.tex, face, 0, wrap), u, v, ox, oy));
+  else out[i] = sglTextureImpl(s, face, u, v, l, ox, oy);
 }
 
 __global__ void sglKatBlendKernel(SglRenderStates rs, const float *src, const float *dst, int n, float *out) {

@@ -224,11 +224,12 @@ template<class Alloc>
 SGL_HD void sglEmitPrim(const SglSetupOut &o, Alloc &alloc, const SglDrawRec &d, int slot, uint32_t key, const SglPrim &p,
                         int i0, int i1, int i2) {
   if (!Alloc::kRecords) { alloc.consume(d, p); return; }   // immediate-mode consumers (depth-only atomic path)
-  o.prims[slot] = p;
   SglPrimVerts pv = {(uint32_t) i0, (uint32_t) i1, (uint32_t) i2, 0u};
   o.primVerts[slot] = pv;
   o.primKeys[slot] = key;
-  alloc.binPrim(slot, p);
+  SglPrim q = p;
+  if (alloc.binPrim(slot, p)) q.flags |= SGL_PF_BIG;
+  o.prims[slot] = q;
 }
 
 // Everything RendererSoft::draw() does for input primitive `i` of draw `drawIdx` between the vertex stage and

@@ -125,7 +125,7 @@ SGL_HD float sglMixF32(uint32_t a, uint32_t b, float f, float omf) {
   memcpy(&x, &a, 4);
   memcpy(&y, &b, 4);
 #endif
-  return xfma(y, f, xmul(x, omf));
+  return xfma(x, omf, xmul(y, f));   // scalar glm::mix<float> as compiled: vmulss y*a; vfmadd231ss x*(1-a) (unit KATs f32_16)
 }
 
 SGL_HD uint32_t sglFloatBits(float f) {

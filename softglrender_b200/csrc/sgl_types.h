@@ -36,6 +36,7 @@ enum { SGL_PK_TRIANGLE = 0, SGL_PK_LINE = 1, SGL_PK_POINT = 2 };
 #define SGL_PF_VALID (1u << 10)
 #define SGL_PF_STEEP (1u << 11)      // line: x/y swapped (RendererSoft.cpp:675-679)
 #define SGL_PF_SWAPPED (1u << 12)    // line: endpoints swapped (RendererSoft.cpp:683-689)
+#define SGL_PF_BIG (1u << 13)        // lives in the pass-wide big list (touches > SGL_BIG_PRIM_TILES tiles, or the bins were full)
 
 // 64-byte primitive record, written by the setup kernel, read by the tile rasteriser
 struct __attribute__((aligned(16))) SglPrim {

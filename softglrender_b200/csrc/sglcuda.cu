@@ -52,6 +52,7 @@ struct Staging {
 
 struct Ctx {
   bool ready = false;
+  int refs = 0;              // sgl_init calls not yet matched by sgl_shutdown (several Renderer objects may share the context)
   int device = 0, rank = 0, world = 1;
   cudaStream_t stream = nullptr;
   bool ownStream = false;
@@ -111,12 +112,19 @@ struct Ctx {
   std::vector<void *> peerAllocs, peerMaps;
   // counters
   unsigned long long *dCounters = nullptr;
+  unsigned int *hOverflow = nullptr;   // pinned, device-visible: set by a kernel that had to DROP geometry (clip arena full)
+  unsigned int *dOverflow = nullptr;   // device alias of hOverflow
+  int clipScale = 1;                   // grows after an overflow: clip-vertex / fan arenas of later passes are this much larger
+  long long binCapLimit = 0, clipMinVerts = 65536, clipMinFans = 32768;   // sgl_debug_set_limits (tests shrink them)
   unsigned long long hostLaunches = 0, hostPasses = 0, hostDraws = 0, hostH2D = 0, hostD2H = 0, hostNsPassEnd = 0, hostNsDraw = 0;
   cudaEvent_t evBegin = nullptr, evEnd = nullptr;
   std::string err;
 };
 
 Ctx g;
+// handles are never reused across a shutdown / init cycle: objects that outlive their renderer (the reference's scene
+// caches do, Viewer.cpp:59-66) then release a dead handle instead of somebody else's resource
+size_t gRetiredBuffers = 1, gRetiredTextures = 1;
 
 int fail(int code, const char *fmt, ...) {
   char buf[512];
@@ -197,6 +205,17 @@ int syncAll() {
   g.auxPending = false;
   g.auxDepthTex.clear();
   return SGL_OK;
+}
+
+// Called after the streams have been drained: a pass that ran out of clip-arena space dropped primitives.  That is
+// reported once as SGL_ERR_OVERFLOW (the reference never drops geometry, so the frame must not pass as good) and the
+// arenas of later passes are enlarged, so a caller that simply retries the frame succeeds.
+int checkOverflow() {
+  if (!g.hOverflow || !*(volatile unsigned int *) g.hOverflow) return SGL_OK;
+  *(volatile unsigned int *) g.hOverflow = 0;
+  if (g.clipScale < 64) g.clipScale *= 2;
+  return fail(SGL_ERR_OVERFLOW, "a render pass ran out of clip-vertex arena space and dropped primitives "
+                                "(sgl_get_counters().clip_overflow); later passes get a %dx larger arena -- resubmit the frame", g.clipScale);
 }
 
 int ensureArena(Ctx::Arena &a, size_t bytes) {
@@ -325,7 +344,12 @@ extern "C" {
 const char *sgl_last_error(void) { return g.err.c_str(); }
 
 int sgl_init(int device_ordinal, int rank, int world) {
-  if (g.ready) return SGL_OK;
+  if (g.ready) {
+    g.refs++;
+    return SGL_OK;
+  }
+  g.buffers.resize(gRetiredBuffers);
+  g.textures.resize(gRetiredTextures);
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0)
@@ -342,6 +366,9 @@ int sgl_init(int device_ordinal, int rank, int world) {
   CU(cudaMemset(g.dCounters, 0, 8 * sizeof(unsigned long long)));
   CU(cudaEventCreate(&g.evBegin));
   CU(cudaEventCreate(&g.evEnd));
+  CU(cudaHostAlloc((void **) &g.hOverflow, 64, cudaHostAllocMapped));
+  memset(g.hOverflow, 0, 64);
+  CU(cudaHostGetDevicePointer((void **) &g.dOverflow, g.hOverflow, 0));
   {  // geometry kernels are small and feed the pixel stage of the NEXT pass: give them priority over resident pixel work
     int lo = 0, hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -377,12 +404,16 @@ int sgl_init(int device_ordinal, int rank, int world) {
     g.noSplit = (ns && atoi(ns) != 0) ? 1 : 0;
   }
   g.ready = true;
+  g.refs = 1;
   g.err.clear();
   return SGL_OK;
 }
 
 int sgl_shutdown(void) {
   if (!g.ready) return SGL_OK;
+  if (--g.refs > 0) return SGL_OK;
+  gRetiredBuffers = g.buffers.size();
+  gRetiredTextures = g.textures.size();
   cudaStreamSynchronize(g.stream);
   for (cudaStream_t gs : g.geomStreams) if (gs) cudaStreamSynchronize(gs);
   for (auto &b : g.buffers)
@@ -414,6 +445,7 @@ int sgl_shutdown(void) {
   for (void *m : g.peerMaps) cudaIpcCloseMemHandle(m);
   for (void *a : g.peerAllocs) cudaFree(a);
   if (g.dCounters) cudaFree(g.dCounters);
+  if (g.hOverflow) cudaFreeHost(g.hOverflow);
   for (auto &s : g.staging) {
     if (s.host) cudaFreeHost(s.host);
     if (s.done) cudaEventDestroy(s.done);
@@ -443,7 +475,7 @@ int sgl_wait_idle(void) {
   NEED_CTX();
   { int rc = syncAll(); if (rc) return rc; }
   CU(cudaStreamSynchronize(g.copyStream));
-  return SGL_OK;
+  return checkOverflow();
 }
 
 int sgl_get_counters(SglCounters *out) {
@@ -463,7 +495,8 @@ int sgl_get_counters(SglCounters *out) {
   out->d2h_bytes = g.hostD2H;
   out->host_ns_pass_end = g.hostNsPassEnd;
   out->host_ns_draw = g.hostNsDraw;
-  return SGL_OK;
+  out->bin_spills = c[1];
+  return checkOverflow();
 }
 
 int sgl_reset_counters(void) {
@@ -709,6 +742,7 @@ int sgl_texture_readback(int handle, int layer, int level, int kind, void *host_
   if (!t || layer < 0 || layer >= t->obj.layers || level < 0 || level >= t->obj.levels) return fail(SGL_ERR_INVALID, "bad texture/layer/level");
   int w = sglLevelDim(t->obj.width, level), h = sglLevelDim(t->obj.height, level);
   CU(cudaStreamSynchronize(g.stream));
+  { int rc = checkOverflow(); if (rc) return rc; }
   if (kind == 1) {
     if (!t->obj.resolve) return fail(SGL_ERR_INVALID, "texture has no resolved colour buffer");
     size_t need = (size_t) w * h * 4;
@@ -717,11 +751,11 @@ int sgl_texture_readback(int handle, int layer, int level, int kind, void *host_
     g.hostD2H += need;
     return SGL_OK;
   }
-  size_t need = (size_t) w * h * 4 * t->obj.samples;
+  size_t need = kind == 2 ? sglLevelTexels(t->obj.layout, w, h) * 4 * t->obj.samples : (size_t) w * h * 4 * t->obj.samples;
   if (bytes < need) return fail(SGL_ERR_INVALID, "readback buffer too small");
   uint8_t *src = levelPtr(*t, layer, level);
   g.hostD2H += need;
-  if (t->obj.layout == SGL_LAYOUT_LINEAR) {
+  if (t->obj.layout == SGL_LAYOUT_LINEAR || kind == 2) {
     CU(cudaMemcpy(host_out, src, need, cudaMemcpyDeviceToHost));
     return SGL_OK;
   }
@@ -773,7 +807,7 @@ int sgl_texture_readback_async(int handle, int layer, int level, int kind, void 
 int sgl_readback_wait(void) {
   NEED_CTX();
   CU(cudaStreamSynchronize(g.copyStream));
-  return SGL_OK;
+  return checkOverflow();
 }
 
 // ---- render pass ----------------------------------------------------------------------------------------------
@@ -913,6 +947,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   size_t oZero = off;
   size_t oDrawCounters = take(sizeof(int32_t) * 2 * std::max(nDraws, 1));
   size_t oBigCount = take(sizeof(uint32_t));
+  size_t oBinReserved = take(sizeof(uint32_t));
   size_t oTileCount = take(sizeof(uint32_t) * nTiles);
   size_t oTileCursor = take(sizeof(uint32_t) * nTiles);
   size_t oTileClassCount = take(sizeof(uint32_t) * SGL_TILE_CLASSES);
@@ -927,12 +962,15 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     r.inputPrims = r.indexCount / per;
     const bool fill = pt == SGL_PRIM_TRIANGLE && r.rs.polygon_mode == SGL_POLY_FILL;
     r.slotsPerPrim = (pt == SGL_PRIM_TRIANGLE && !fill) ? 3 : 1;
+    // clip arena: a filled triangle allocates at most 12 vertices (2 per frustum plane) and appends at most 6 fan
+    // triangles; that worst case is reserved outright for draws of up to ~5 k triangles, larger draws get 2 vertices + 1
+    // fan triangle per input triangle (x clipScale, which doubles after an overflow was reported -- checkOverflow)
     int extraVerts;
-    if (fill) extraVerts = (int) std::min<long long>(12LL * r.inputPrims, std::max<long long>(4096, 2LL * r.inputPrims));
+    if (fill) extraVerts = (int) std::min<long long>(12LL * r.inputPrims, std::max<long long>(g.clipMinVerts, 2LL * g.clipScale * r.inputPrims));
     else if (pt == SGL_PRIM_POINT) extraVerts = 0;
     else extraVerts = (pt == SGL_PRIM_LINE ? 2 : 6) * r.inputPrims;
     r.vertexCap = r.vertexCount + extraVerts;
-    r.appendCap = fill ? (int) std::min<long long>(6LL * r.inputPrims, std::max<long long>(1024, r.inputPrims)) : 0;
+    r.appendCap = fill ? (int) std::min<long long>(6LL * r.inputPrims, std::max<long long>(g.clipMinFans, (long long) g.clipScale * r.inputPrims)) : 0;
     r.primBase = primSlots;
     r.appendBase = primSlots + r.inputPrims * r.slotsPerPrim;
     primSlots = r.appendBase + r.appendCap;
@@ -953,6 +991,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   size_t oPrimKeys = take(sizeof(uint32_t) * std::max(primSlots, 1));
   size_t oBigList = take(sizeof(uint32_t) * std::max(primSlots, 1));
   size_t binCapacity = std::min<size_t>(std::max<size_t>((size_t) primSlots * 8, 1 << 20), (size_t) 1 << 29);
+  if (g.binCapLimit > 0) binCapacity = std::min<size_t>(binCapacity, (size_t) g.binCapLimit);
   // depth-only path: the region holds 64-byte work items instead (>= 2 per primitive slot + one per 512 framebuffer pixels)
   if (depthOnly) binCapacity = ((size_t) primSlots * 2 + (size_t) fbW * fbH / 512 + 65536) * (sizeof(SglPrim) / sizeof(uint32_t));
   size_t oBins = take(sizeof(uint32_t) * binCapacity);
@@ -1092,6 +1131,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     D.largeCount = P.tileCount;          // zero-initialised with the rest of the counter block
     D.largeCapacity = (uint32_t) std::max(primSlots, 1);
     D.counters = g.dCounters;
+    D.overflowHost = g.dOverflow;
     D.tileOwner = P.tileOwner;
     D.tilesX = tilesX;
     D.rank = g.rank;
@@ -1123,6 +1163,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
       SglSetupOut so = {(SglPrim *) (A + oPrims), (SglPrimVerts *) (A + oPrimVerts), (uint32_t *) (A + oPrimKeys)};
       SglSetupShared ss;
       ss.tileCount = P.tileCount; ss.bigList = P.bigList; ss.bigCount = P.bigCount; ss.bigCapacity = P.bigCapacity;
+      ss.binReserved = (uint32_t *) (A + oBinReserved); ss.binCapacity = P.binCapacity; ss.overflowHost = g.dOverflow;
       ss.counters = g.dCounters; ss.tilesX = tilesX; ss.tilesY = tilesY; ss.fbW = fbW; ss.fbH = fbH;
       ss.tileOwner = P.tileOwner; ss.rank = g.rank;
       rc = launch("sglSetupKernel", sglSetupKernel, dim3((maxPrims + 127) / 128, nDraws), dim3(128), P.draws, so, ss, dt ? 1 : 0);
@@ -1232,6 +1273,18 @@ int sgl_pass_end(void) {
   g.hostPasses++;
   g.draws.clear();
   return rc;
+}
+
+// testing aid: shrink the tile-bin region and the minimum clip arenas so that the spill / overflow paths can be exercised
+// with small inputs (0 / negative = default)
+int sgl_debug_set_limits(long long bin_capacity, long long clip_min_vertices, long long clip_min_fans) {
+  NEED_CTX();
+  { int rc = syncAll(); if (rc) return rc; }
+  g.binCapLimit = bin_capacity > 0 ? bin_capacity : 0;
+  g.clipMinVerts = clip_min_vertices > 0 ? clip_min_vertices : 65536;
+  g.clipMinFans = clip_min_fans > 0 ? clip_min_fans : 32768;
+  g.clipScale = 1;
+  return SGL_OK;
 }
 
 // instrumentation: per-tile primitive list lengths of the most recent colour pass (SGL_TILE_UNSORTED = overflow tile)
@@ -1385,7 +1438,8 @@ int sgl_peer_free(void *ptr) {
   NEED_CTX();
   auto it = std::find(g.peerAllocs.begin(), g.peerAllocs.end(), ptr);
   if (it == g.peerAllocs.end()) return fail(SGL_ERR_INVALID, "not a peer allocation");
-  CU(cudaStreamSynchronize(g.stream));
+  { int rc = syncAll(); if (rc) return rc; }
+  CU(cudaStreamSynchronize(g.copyStream));
   CU(cudaFree(ptr));
   g.peerAllocs.erase(it);
   return SGL_OK;
@@ -1450,7 +1504,8 @@ int sgl_peer_wait(const void *flags_device_ptr, int count, uint32_t value, int t
 int sgl_peer_timeouts(uint64_t *count_out) {
   NEED_CTX();
   unsigned long long c = 0;
-  CU(cudaStreamSynchronize(g.stream));
+  { int rc = syncAll(); if (rc) return rc; }
+  CU(cudaStreamSynchronize(g.copyStream));
   CU(cudaMemcpy(&c, g.dCounters + 6, sizeof(c), cudaMemcpyDeviceToHost));
   *count_out = c;
   return SGL_OK;
@@ -1474,23 +1529,29 @@ int sgl_kat_barycentric(const float *tri_xyzw, const float *sample_xy, int n, fl
   return SGL_OK;
 }
 
-int sgl_kat_sample(int texture, int filter_min, int wrap, int border, const float *coords, const float *lod, int n,
-                   uint32_t *out) {
+int sgl_kat_sample(int texture, int filter_min, int wrap, int border, const float *coords, const float *lod,
+                   const int32_t *offsets_xy, int n, int split_phase, uint32_t *out) {
   NEED_CTX();
   TextureRec *t = tex(texture);
   if (!t) return fail(SGL_ERR_INVALID, "bad texture handle %d", texture);
   int comps = t->obj.layers == 6 ? 3 : 2;
+  if (split_phase && !(t->obj.format == SGL_FMT_RGBA8 && t->obj.samples == 1 && t->obj.layout == SGL_LAYOUT_LINEAR &&
+                       filter_min == SGL_FILTER_LINEAR && (wrap == SGL_WRAP_REPEAT || wrap == SGL_WRAP_CLAMP_TO_EDGE)))
+    return fail(SGL_ERR_INVALID, "split-phase taps need a simple sampler");
   DevTmp<float> dC, dL;
   DevTmp<uint32_t> dO;
-  CU(dC.alloc((size_t) comps * n)); CU(dL.alloc(n)); CU(dO.alloc(n));
+  DevTmp<int32_t> dOff;
+  CU(dC.alloc((size_t) comps * n)); CU(dL.alloc(n)); CU(dO.alloc(n)); CU(dOff.alloc((size_t) 2 * n));
   CU(cudaMemcpy(dC.p, coords, sizeof(float) * comps * n, cudaMemcpyHostToDevice));
   if (lod) CU(cudaMemcpy(dL.p, lod, sizeof(float) * n, cudaMemcpyHostToDevice));
+  if (offsets_xy) CU(cudaMemcpy(dOff.p, offsets_xy, sizeof(int32_t) * 2 * n, cudaMemcpyHostToDevice));
   uint32_t b;
   float bf = border == SGL_BORDER_WHITE ? 1.f : 0.f;
   if (t->obj.format == SGL_FMT_FLOAT32) memcpy(&b, &bf, 4);
   else b = border == SGL_BORDER_WHITE ? 0xFFFFFFFFu : 0u;
   int rc = launch("sglKatSampleKernel", sglKatSampleKernel, dim3((n + 127) / 128), dim3(128), (const SglTexObj *) g.dTextures, texture, filter_min, wrap, b,
-                  (const float *) dC.p, lod ? (const float *) dL.p : (const float *) nullptr, n, dO.p);
+                  (const float *) dC.p, lod ? (const float *) dL.p : (const float *) nullptr,
+                  offsets_xy ? (const int32_t *) dOff.p : (const int32_t *) nullptr, n, split_phase, dO.p);
   if (rc) return rc;
   CU(cudaStreamSynchronize(g.stream));
   CU(cudaMemcpy(out, dO.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));

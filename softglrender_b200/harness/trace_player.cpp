@@ -19,6 +19,23 @@ struct Rd {
 };
 }  // namespace
 
+TracePlayer::~TracePlayer() {
+  if (out_) fclose(out_);
+  out_ = nullptr;
+  if (!renderer_) return;
+  renderer_->waitIdle();
+  resources_.clear();
+  fbos_.clear();
+  samplers_.clear();
+  blocks_.clear();
+  pipelines_.clear();
+  programs_.clear();
+  vaos_.clear();
+  textures_.clear();
+  renderer_->destroy();
+  renderer_ = nullptr;
+}
+
 bool TracePlayer::load(const std::string &path) {
   FILE *f = fopen(path.c_str(), "rb");
   if (!f) {

@@ -32,6 +32,7 @@ int nativeHandle(SoftGL::Texture &tex);   // C-ABI handle for RendererCUDA, -1 e
 
 class TracePlayer {
  public:
+  ~TracePlayer();   // Viewer::destroy order (Viewer.cpp:59-88): waitIdle, release every resource, then Renderer::destroy
   bool load(const std::string &path);
   void setDataDir(const std::string &dir) { dataDir_ = dir; }
   void setOutput(const std::string &path) { outPath_ = path; }

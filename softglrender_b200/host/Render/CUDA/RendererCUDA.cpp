@@ -265,10 +265,18 @@ bool RendererCUDA::create() {
     logError("create");
     return false;
   }
+  created_ = true;
   return true;
 }
 
-void RendererCUDA::destroy() { sgl_wait_idle(); }
+// Renderer::destroy (Renderer.h:28): releases this renderer's reference on the device context (sgl_shutdown frees every
+// device resource once the last renderer is gone)
+void RendererCUDA::destroy() {
+  if (!created_) return;
+  created_ = false;
+  sgl_wait_idle();
+  sgl_shutdown();
+}
 
 std::shared_ptr<FrameBuffer> RendererCUDA::createFrameBuffer(bool offscreen) { return std::make_shared<FrameBufferCUDA>(offscreen); }
 

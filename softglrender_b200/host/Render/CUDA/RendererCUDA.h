@@ -12,6 +12,13 @@
 
 namespace SoftGL {
 
+// RendererType of this backend.  The reference's enum (Render/Renderer.h:18-22) ends at Renderer_Vulkan; a tree that adds a
+// `Renderer_CUDA` enumerator there defines SGL_HAVE_RENDERER_CUDA_ENUM, otherwise the next free
+// value is used, so this header compiles against the UNMODIFIED reference headers (tests/test_boundary_compiles.py).
+#ifndef SGL_HAVE_RENDERER_CUDA_ENUM
+static const RendererType Renderer_CUDA = static_cast<RendererType>(Renderer_Vulkan + 1);
+#endif
+
 // View::ShadingModel values (src/Viewer/Material.h:25-34) == SGL_SHADER_* ids
 enum ShaderKindCUDA {
   ShaderCUDA_None = 0, ShaderCUDA_BaseColor = 1, ShaderCUDA_BlinnPhong = 2, ShaderCUDA_PBR = 3, ShaderCUDA_Skybox = 4,
@@ -61,7 +68,7 @@ class FrameBufferCUDA : public FrameBuffer {
 class VertexArrayObjectCUDA : public VertexArrayObject {
  public:
   explicit VertexArrayObjectCUDA(const VertexArray &va);
-  ~VertexArrayObjectCUDA() override;
+  ~VertexArrayObjectCUDA();   // not an override: the reference's VertexArrayObject has no virtual destructor (Vertex.h:15-19)
   int getId() const override { return id_; }
   void updateVertexData(void *data, size_t length) override;
   int vertexBuffer = 0, indexBuffer = 0;
@@ -150,6 +157,7 @@ class RendererCUDA : public Renderer {
   int device_ = 0, rank_ = 0, world_ = 1;
   int textureLayout_ = 0;
   bool passOpen_ = false;
+  bool created_ = false;
   VertexArrayObjectCUDA *vao_ = nullptr;
   ShaderProgramCUDA *program_ = nullptr;
   const RenderStates *states_ = nullptr;

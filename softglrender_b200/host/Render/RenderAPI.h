@@ -72,7 +72,6 @@ struct FrameBufferAttachment {
 class FrameBuffer {
  public:
   explicit FrameBuffer(bool offscreen) : offscreen_(offscreen) {}
-  virtual ~FrameBuffer() = default;
   virtual int getId() const = 0;
   virtual bool isValid() = 0;
 
@@ -105,7 +104,6 @@ class FrameBuffer {
 // ---- Vertex.h ---------------------------------------------------------------------------------------------------------
 class VertexArrayObject {
  public:
-  virtual ~VertexArrayObject() = default;
   virtual int getId() const = 0;
   virtual void updateVertexData(void *data, size_t length) = 0;
 };
@@ -129,7 +127,6 @@ class ShaderProgram;
 class Uniform {
  public:
   explicit Uniform(std::string n) : name(std::move(n)), hash_(nextHash()++) {}
-  virtual ~Uniform() = default;
   int getHash() const { return hash_; }
   virtual int getLocation(ShaderProgram &program) = 0;
   virtual void bindProgram(ShaderProgram &program, int location) = 0;
@@ -169,7 +166,6 @@ class ShaderResources {
 // ---- ShaderProgram.h -------------------------------------------------------------------------------------------------------
 class ShaderProgram {
  public:
-  virtual ~ShaderProgram() = default;
   virtual int getId() const = 0;
   virtual void addDefine(const std::string &def) = 0;
   virtual void addDefines(const std::set<std::string> &defs) {
@@ -248,11 +244,10 @@ class PipelineStates {
 };
 
 // ---- Renderer.h --------------------------------------------------------------------------------------------------------------
-enum RendererType { Renderer_SOFT, Renderer_OPENGL, Renderer_Vulkan, Renderer_CUDA };
+enum RendererType { Renderer_SOFT, Renderer_OPENGL, Renderer_Vulkan };   // Renderer.h:18-22 (Renderer_CUDA: RendererCUDA.h)
 
 class Renderer {
  public:
-  virtual ~Renderer() = default;
   virtual RendererType type() = 0;
   virtual bool create() { return true; }
   virtual void destroy() {}

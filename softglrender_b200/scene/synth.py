@@ -324,6 +324,77 @@ def soup_trace(n_tris=100000, width=1920, height=1080, seed=0x5EED, n_textures=8
     return w
 
 
+def stress_trace(kind, width=512, height=384, n_tris=600, msaa=False, seed=5):
+    """Capacity stress cases for the binning / clipping arenas (the reference never drops geometry):
+    kind "mid"     -- many mid-size triangles whose pixel range spans 20-60 16x16 tiles each (bin pressure)
+    kind "clipped" -- every triangle pokes through the near plane and usually a side plane (clip-vertex / fan pressure)
+    Flat-shaded (ShaderBasic), depth-tested, 8 draws with different colours."""
+    w = T.TraceWriter()
+    rs = np.random.RandomState(seed)
+    cam = Camera(60.0, float(width) / float(height), 0.5)
+    cam.look_at((0, 0, 0), (0, 0, -1), (0, 1, 0))
+    mvp = cam.projection() @ cam.view()
+    eye4 = np.eye(4, dtype=np.float32)
+    color = w.create_texture(width, height, T.TextureType_2D, T.TextureFormat_RGBA8,
+                             T.TextureUsage_AttachmentColor | T.TextureUsage_RendererOutput, False, msaa)
+    w.tex_init(color)
+    depth = w.create_texture(width, height, T.TextureType_2D, T.TextureFormat_FLOAT32, T.TextureUsage_AttachmentDepth, False, msaa)
+    w.tex_init(depth)
+    fbo = w.create_fbo(False)
+    w.fbo_color(fbo, color, 0)
+    w.fbo_depth(fbo, depth)
+    th = math.tan(math.radians(30.0))
+    aspect = float(width) / height
+    pos = np.zeros((n_tris, 3, 3), np.float32)
+    if kind == "mid":
+        z = -rs.uniform(2.0, 20.0, n_tris).astype(np.float32)
+        cx = rs.uniform(-1, 1, n_tris).astype(np.float32) * (-z) * th * aspect
+        cy = rs.uniform(-1, 1, n_tris).astype(np.float32) * (-z) * th
+        edge_px = rs.uniform(70.0, 120.0, n_tris).astype(np.float32)          # 5..8 tiles per axis
+        edge = edge_px * (-z) * th * 2.0 / height
+        ang = rs.uniform(0, 2 * math.pi, n_tris).astype(np.float32)
+        for k in range(3):
+            a = ang + k * (2 * math.pi / 3)
+            pos[:, k, 0] = cx + np.cos(a) * edge * 0.6
+            pos[:, k, 1] = cy + np.sin(a) * edge * 0.6
+            pos[:, k, 2] = z + rs.uniform(-0.2, 0.2, n_tris).astype(np.float32)
+    elif kind == "clipped":
+        for k in range(3):
+            pos[:, k, 0] = rs.uniform(-6, 6, n_tris)
+            pos[:, k, 1] = rs.uniform(-4, 4, n_tris)
+        pos[:, 0, 2] = rs.uniform(0.1, 2.0, n_tris)       # behind the camera
+        pos[:, 1, 2] = -rs.uniform(0.8, 4.0, n_tris)      # in front
+        pos[:, 2, 2] = -rs.uniform(0.8, 4.0, n_tris)
+    else:
+        raise ValueError(kind)
+    b_model = w.create_block("UniformsModel", 256)
+    b_mat = w.create_block("UniformsMaterial", 48)
+    w.block_data(b_model, pack_uniforms_model(False, eye4, mvp, np.eye(3), eye4))
+    prog = w.create_program(T.Shading_BaseColor, [])
+    st = T.RenderStates()
+    st.depthTest = True
+    pipe = w.create_pipeline(st)
+    MB, TB = T.UniformBlock_Model, T.UniformBlock_Material
+    n_draws = 8
+    vaos = []
+    for i in range(n_draws):
+        p = pos[i::n_draws].reshape(-1, 3)
+        vaos.append(w.create_vao(_verts(p), np.arange(len(p), dtype=np.int32)))
+    w.frame_begin()
+    w.begin_pass(fbo, True, True, (0.05, 0.05, 0.1, 1.0), 1.0)
+    w.viewport(0, 0, width, height)
+    for i, vao in enumerate(vaos):
+        w.block_data(b_mat, pack_uniforms_material(False, False, False, 1.0, 1.0,
+                                                   (0.2 + 0.1 * i, 1.0 - 0.11 * i, 0.3 + 0.05 * (i % 3), 1.0)))
+        w.draw(vao, prog, pipe, {MB: b_model, TB: b_mat}, {})
+    w.end_pass()
+    w.frame_end()
+    w.wait_idle()
+    w.readback(color, "color")
+    w.readback(depth, "depth")
+    return w
+
+
 def edge_trace(msaa=False):
     """Degenerate inputs the API must take in its stride: a render pass without draws (clear only), a draw with no
     indices, a 1x1 and a 3x2 framebuffer, a viewport smaller than / offset inside the framebuffer's tile grid, a pass

@@ -24,6 +24,8 @@ FIXTURES = {
     "kat_ms4_revz": (lambda ad: synth.kat_trace(192, 128, msaa=True, reverse_z=True, seed=11), False),
     "kat_nomip_odd": (lambda ad: synth.kat_trace(161, 97, msaa=True, reverse_z=False, seed=23, mipmaps=False), False),
     "c1_cube_200x160": (lambda ad: scenes.config1_cube(ad, 200, 160), True),
+    # ShaderSkybox with EQUIRECTANGULAR_MAP (atan2 / asin, SkyboxSoft.h:83-98) sampling Room.jpeg directly: pbrIbl off
+    "sky_equirect_200x120": (lambda ad: scenes.config2_helmet(ad, width=200, height=120, skybox="Room", model="Cube", pbr_ibl=False), True),
     # degenerate inputs: clear-only pass, empty draw, 1x1 / 3x2 targets, small viewport, load pass with a leading blended
     # draw, zero-area and fully clipped triangles, empty depth-only pass
     "edge_1x": (lambda ad: synth.edge_trace(msaa=False), False),

@@ -317,7 +317,7 @@ int sgl_pass_end(void) {
   return 0;
 }
 int sgl_kat_barycentric(const float *, const float *, int, float *, int *, float *) { return -1; }
-int sgl_kat_sample(int, int, int, int, const float *, const float *, int, uint32_t *) { return -1; }
+int sgl_kat_sample(int, int, int, int, const float *, const float *, const int32_t *, int, int, uint32_t *) { return -1; }
 int sgl_kat_blend(const SglRenderStates *, const float *, const float *, int, float *) { return -1; }
 int sgl_kat_depth(int, const float *, const float *, int, int *) { return -1; }
 }

@@ -15,7 +15,7 @@ def main():
     capi.init(0)
     lib = capi.load()
     work = os.path.join(ROOT, "build", "bench")
-    workloads.build_c2(work, 1920, 1080)               # makes the IBL maps
+    ibl_files = workloads.build_ibl(work)              # makes the IBL maps
     ad = workloads.assets_dir()
     variants = {"full": {}, "no_skybox": dict(show_skybox=False), "no_axis": dict(world_axis=False), "no_floor": dict(show_floor=False),
                 "no_light_point": dict(show_light=False), "cube_model": dict(_model="Cube"), "no_shadow": dict(shadow_map=False)}
@@ -23,7 +23,7 @@ def main():
         cfg = dict(cfg)
         model = cfg.pop("_model", "DamagedHelmet")
         trace = os.path.join(work, "c2var_%s.sglt" % name)
-        scenes.config2_helmet(ad, 1920, 1080, ibl_files=workloads.IBL_FILES, model=model, **cfg).save(trace)
+        scenes.config2_helmet(ad, 1920, 1080, ibl_files=ibl_files, model=model, **cfg).save(trace)
         p = capi.Player(trace, work)
         p.setup()
         for _ in range(5):
