@@ -39,6 +39,7 @@ def limits():
     yield lambda b=0, v=0, f=0: capi.check(lib.sgl_debug_set_limits(b, v, f))
     lib.sgl_wait_idle()
     capi.check(lib.sgl_debug_set_limits(0, 0, 0))
+    lib.sgl_reset_counters()      # the overflow counts provoked here must not leak into other tests' assertions
 
 
 @pytest.mark.parametrize("msaa", [False, True])
