@@ -123,6 +123,32 @@ def cpu_reference_fps(trace, data_dir, frames, warmup):
             "sample": "%d timed frames of the same config-2 trace (median), %d warm-up, %.0f s wall" % (frames, warmup, time.time() - t0)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pins this rank's threads to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is allocated
+    (first touch then places the pages on that node).  With N ranks reading 8.3 MB frames back per step, buffers on the
+    wrong socket make every device->host copy cross the inter-socket link (round 1: e2e weak scaling 0.52 at N = 8)."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"node": None, "reason": "no NUMA information for %s" % bus}
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return {"node": node, "reason": "no allowed CPU on the GPU's node"}
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed)}
+    except Exception as e:
+        return {"node": None, "reason": str(e)[:80]}
+
+
 def _json_only_stdout():
     """The contract is ONE JSON line on stdout: everything else a library may print there (NCCL's version banner, ...) is
     sent to stderr by pointing fd 1 at fd 2; the returned writer is the original stdout."""
@@ -165,9 +191,16 @@ def main():
         # the IBL maps are inputs: generate them with whatever renderer is available on this box
         ibl_player = workloads.CUDA_PLAYER if _cuda_ok() else (workloads.REF_PLAYER if os.path.exists(workloads.REF_PLAYER) else None)
         trace, data = workloads.build_c2(work, WIDTH, HEIGHT, ibl_player=ibl_player)
-        frames = min(K, 60)
-        cb = cpu_reference_fps(trace, data, frames, min(W, 3))
-        line = {"metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": frames, "warmup": min(W, 3),
+        # one step = one whole frame on all host cores (~0.13 s on 16 cores); --steps / --warmup are honoured as long as
+        # the run stays within a few minutes (a 2-frame probe sizes it), else the number of timed frames is cut and said so
+        probe = cpu_reference_fps(trace, data, 2, 1)
+        budget_s = 240.0
+        frames = max(3, min(K, int(budget_s / max(probe["ms_per_frame"] / 1e3, 1e-3)) - W))
+        cb = cpu_reference_fps(trace, data, frames, W)
+        if frames < K:
+            cb["sample"] += "; --steps %d cut to %d frames to keep the reference arm within ~%d s" % (K, frames, int(budget_s))
+        config["gather"] = "n/a"
+        line = {"metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": frames, "warmup": W,
                 "ms_per_step": cb["ms_per_frame"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "bundled glTF asset + synthetic camera (Config defaults)", "config": config, "impl": "reference",
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -185,6 +218,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; RendererCUDA has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    host_numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "n/a"
     ctl = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -304,9 +338,11 @@ def main():
     flush_store(False)
     sync_all()
 
-    # ---- timed region 1: device-resident throughput (CUDA events on the library's stream), max over ranks
-    capi.check(lib.sgl_reset_counters())
-    with ClockSampler(local_rank) as clocks:
+    # ---- timed region 1: device-resident throughput (CUDA events on the library's stream), max over ranks.
+    #      `value` comes from the FIRST region of exactly K steps; the region is then repeated (untimed for `value`) until
+    #      ~0.4 s of frames have run, so that a short K (the driver's --steps 20 is a 6 ms window) still comes with a spread
+    #      and with clock samples taken under the same load.
+    def timed_region():
         ms = C_float()
         sync_all()
         capi.check(lib.sgl_timer_begin())
@@ -315,9 +351,20 @@ def main():
         flush_store(False)
         capi.check(lib.sgl_timer_end(ms))
         sync_all()
-        elapsed_ms = _max_over_ranks(ms.value, world)
-    ctr = capi.counters()
+        return _max_over_ranks(ms.value, world)
+
+    capi.check(lib.sgl_reset_counters())
+    with ClockSampler(local_rank) as clocks:
+        elapsed_ms = timed_region()
+        ctr = capi.counters()
+        n_rep = int(min(max(400.0 / max(elapsed_ms, 1e-3), 2), 12))
+        if world > 1:
+            t = torch.tensor([n_rep], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            n_rep = int(t.item())
+        reps = sorted(timed_region() / K for _ in range(n_rep))
     clocks_summary = clocks.summary()
+    spread = {"repeats_of_K_steps": n_rep, "ms_per_step_min": reps[0], "ms_per_step_median": reps[len(reps) // 2], "ms_per_step_max": reps[-1]}
 
     # ---- timed region 2: end to end through the public API with host buffers: per frame the draw records / uniform
     #      snapshots are uploaded from pinned memory and the finished frame is read back into pinned host memory
@@ -357,9 +404,9 @@ def main():
             "gfrag_per_s": fps * frags_per_frame / 1e9, "fragments_per_frame": frags_per_frame,
             "e2e": {"value": frames_per_step * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d // K,
                     "d2h_bytes_per_step": d2h // K},
-            "gpu_launches": launches, "clocks": clocks_summary, "host_submit_ms_per_step": host_submit_ms}
+            "gpu_launches": launches, "clocks": clocks_summary, "host_submit_ms_per_step": host_submit_ms, "spread": spread, "host_numa": host_numa}
     if rank == 0:
-        line["roofline"] = roofline_block(ktimes, ctr, K)
+        line.update(roofline_blocks(ktimes, ctr, K, elapsed_ms / K, frames_per_step, tiles, world))
         line["kernel_ms_per_frame"] = {k: v[1] / 20.0 for k, v in sorted(ktimes.items())}
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -407,50 +454,86 @@ def _max_over_ranks(v, world):
     return float(t.item())
 
 
-def roofline_block(ktimes, ctr, K):
-    """Roofline of the dominant kernel (largest share of the step; DESIGN.md section 6 states the per-unit figures).
+def _offline_json(name):
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            return json.load(f)
+    except Exception:
+        return None
 
-    Algorithmic bytes per launch = what the kernel must move once, with perfect reuse:
-      sglShadeKernel<4>  owners in 16 B/px + per-sample colour out 16 B/px + resolved colour out 4 B/px
-                         + unique texels: min(level-0 bytes of the bound maps, 16 B x fragments) for the skybox cube,
-                           level-0 bytes of the 5 material maps + the two IBL cubes
-                         + primitive records (64 + 16 B) of binned primitives + referenced vertex varyings (128 B)
-      sglVisKernel<4>    per-sample depth out 16 B/px + owners out 16 B/px + binned primitive records (64 + 4 + 4 B)
-    Peak = MEASURED_PEAKS.json hbm_gbs (burst copy figure: the kernel is timed alone between events); `traffic` = measured
-    dram__bytes_read.sum + dram__bytes_write.sum of that kernel per launch from the committed ncu --set full capture."""
-    name = max(ktimes, key=lambda k: ktimes[k][1])
-    launches, total_ms = ktimes[name]
-    avg_ms = total_ms / max(launches, 1)
-    binned = ctr["primitives_binned"] / float(K)
-    frags = ctr["fragments_shaded"] / float(K)
-    px = WIDTH * HEIGHT
-    if name.startswith("sglShade"):
-        b_tex = min(6 * 2000 * 2000 * 4, 16.0 * frags) + 5 * 1024 * 1024 * 4 + 524280 + 24576
-        b_alg = px * (16 + 16 + 4) + b_tex + binned * (64 + 16) + 14556 * 128
-        what = "owners in + MSAA colour/resolve out + unique texels + primitive records/varyings"
-    elif name.startswith("sglVis"):
-        b_alg = px * (16 + 16) + binned * (64 + 4 + 4)
-        what = "MSAA depth out + owners out + binned primitive records"
-    else:
-        b_alg = px * (16 + 16 + 4) + binned * (64 + 16 + 4) + 14556 * 128
-        what = "attachments out + primitive records"
+
+def roofline_blocks(ktimes, ctr, K, ms_per_step, frames_per_step, tiles, world):
+    """Roofline per SURVEY.md 8d / DESIGN.md section 6.  HBM is the bounding resource of this path (no dense contraction);
+    algorithmic bytes = what MUST cross HBM once with perfect on-chip reuse:
+
+      B_geom = 64 B x VAO vertices + 4 B x indices of every draw incl. the shadow pass   (counters of this run)
+      B_tex  = unique texel bytes the frame's samplers touch: MEASURED with the touched-sector bitmap of the instrumentation
+               build (tools/gpu/texel_touch.py -> profiles/r02_texel_touch_c2.json); upper bound = level-0 bytes of the bound maps
+      B_out  = 4 B x W x H resolved colour (+ the 512^2 float shadow map written and read once)
+      B_ms   = 0: multisample colour / depth / visibility live on chip in the ideal pipeline
+
+    Per kernel: sglShadeKernel must read B_tex and write the resolved colour; sglVisKernel must read one 64-byte record per
+    primitive that reaches rasterisation.  Everything else either kernel moves today (per-sample depth, owners, per-sample
+    colour) is pipeline-internal traffic and shows up in `traffic` (ncu dram bytes), not in the algorithmic figure.
+    `achieved` = algorithmic bytes / the kernel's average duration measured live with CUDA events in this run.
+    The dominant kernel (largest share of the step, wait kernels of the multi-GPU gather excluded) is `roofline`."""
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peak, src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+            peak, src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy figure: kernels are timed alone between events)"
     except Exception:
         peak, src = 6650.0, "B200_PROFILING.md fallback"
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
-            traffic = json.load(f)["kernels"][name.split("<")[0]]["dram_bytes_per_launch"]
-    except Exception:
-        pass
-    achieved = b_alg / 1e9 / (avg_ms / 1e3)
-    return {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": b_alg, "algorithmic_bytes_are": what,
-            "peak_source": src,
-            "note": "this path is latency/issue bound at 1080p, not HBM bound (SURVEY 8d predicted ~1%% of roofline): see "
-                    "profiles/README.md for the ncu stall breakdown; %.0f MB compulsory per launch" % (b_alg / 1e6)}
+    frames = float(K) * (1 if (tiles or world == 1) else 1)      # counters are per rank: K frames each
+    px = WIDTH * HEIGHT
+    verts = ctr["vertices_in"] / frames
+    idx = ctr["indices_in"] / frames
+    prims = ctr["primitives_in"] / frames
+    b_geom = 64.0 * verts + 4.0 * idx
+    touch = _offline_json("r02_texel_touch_c2.json")
+    level0 = 6 * 2000 * 2000 * 4 + 5 * 1024 * 1024 * 4 + 524280 + 24576 + 512 * 512 * 4
+    if touch and "unique_texel_bytes_per_frame" in touch:
+        b_tex, tex_src = float(touch["unique_texel_bytes_per_frame"]), "measured: touched 32-byte sectors (profiles/r02_texel_touch_c2.json, git %s)" % touch.get("git")
+    else:
+        b_tex, tex_src = float(min(level0, 16.0 * ctr["fragments_shaded"] / frames + 5 * 1024 * 1024 * 4)), "upper bound: min(level-0 bytes of the bound maps, 16 B x fragments)"
+    b_out = 4.0 * px + 2 * 512 * 512 * 4
+    ncu = _offline_json("ncu_summary.json") or {}
+
+    def block(name, b_alg, what, avg_ms):
+        achieved = b_alg / 1e9 / (avg_ms / 1e3)
+        blk = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+               "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": b_alg, "algorithmic_bytes_are": what, "traffic": None}
+        k = (ncu.get("kernels") or {}).get(name.split("<")[0])
+        if k:   # offline: one `ncu --set full` capture of the same command, committed under profiles/
+            blk["traffic"] = k.get("dram_bytes_per_launch")
+            top = sorted((k.get("stall_per_issue") or {}).items(), key=lambda kv: -kv[1])
+            top = [t for t in top if t[0] != "selected"][:2]
+            blk["offline_ncu"] = {"source": "profiles/ncu_summary.json (%s)" % ncu.get("source"), "issue_active_pct": k.get("issue_active_pct"),
+                                  "warps_active_pct": k.get("warps_active_pct"), "top_stalls_per_issue": dict(top),
+                                  "registers_per_thread": k.get("registers_per_thread")}
+        return blk
+
+    cands = {k: v for k, v in ktimes.items() if not k.startswith("sglPeer")}
+    blocks = []
+    for name, (launches, total_ms) in sorted(cands.items(), key=lambda kv: -kv[1][1]):
+        avg = total_ms / max(launches, 1)
+        if name.startswith("sglShade"):
+            blocks.append(block(name, b_tex + 4.0 * px, "unique texel sectors in + resolved colour out", avg))
+        elif name.startswith("sglVis"):
+            blocks.append(block(name, 64.0 * prims, "one 64-byte record per primitive in (depth / owners stay on chip in the ideal)", avg))
+        elif name.startswith("sglRaster"):
+            blocks.append(block(name, b_tex + 4.0 * px + 64.0 * prims, "primitive records + unique texel sectors in, resolved colour out", avg))
+    frame_b = b_geom + b_tex + b_out
+    frame_ms = ms_per_step / float(frames_per_step)
+    out = {"roofline": blocks[0] if blocks else None,
+           "roofline_kernels": blocks[1:3],
+           "roofline_frame": {"bound": "hbm", "algorithmic_bytes_per_frame": frame_b, "b_geom": b_geom, "b_tex": b_tex, "b_out": b_out, "b_ms": 0,
+                              "b_tex_source": tex_src, "achieved": frame_b / 1e9 / (frame_ms / 1e3), "peak": peak, "unit": "GB/s",
+                              "frac": frame_b / 1e9 / (frame_ms / 1e3) / peak, "peak_source": src,
+                              "roofline_ms_per_frame": frame_b / 1e9 / peak * 1e3}}
+    if out["roofline"]:
+        out["roofline"]["peak_source"] = src
+        out["roofline"]["note"] = ("HBM is not what binds this path at 1080p (SURVEY 8d: a frame needs %.0f MB, %.1f us at the measured peak): the "
+                                   "kernels are latency / issue bound -- see offline_ncu and profiles/README.md" % (frame_b / 1e6, frame_b / 1e9 / peak * 1e6))
+    return out
 
 
 if __name__ == "__main__":

@@ -105,6 +105,8 @@ typedef struct SglCounters {
   uint64_t host_ns_pass_end;  /* CPU time spent inside sgl_pass_end (arena layout, uploads, launches) */
   uint64_t host_ns_draw;      /* CPU time spent inside sgl_draw (state snapshot) */
   uint64_t bin_spills;        /* primitives that went to the pass-wide list because the tile bins were full (correct, slower) */
+  uint64_t vertices_in;       /* VAO vertices of all submitted draws (64 B each) ... */
+  uint64_t indices_in;        /* ... and their indices (4 B each): B_geom of the roofline = 64 * vertices_in + 4 * indices_in */
 } SglCounters;
 
 /* ---- context ---------------------------------------------------------------------------------------- */
@@ -135,6 +137,9 @@ int sgl_debug_tile_times(int enable, unsigned long long *out, int capacity_tiles
 /* testing aid: cap the tile-bin region (entries) and the minimum clip arenas (vertices, fan triangles) of later passes so
  * that the bin-spill and clip-overflow paths can be exercised with small inputs; 0 restores a default */
 int sgl_debug_set_limits(long long bin_capacity, long long clip_min_vertices, long long clip_min_fans);
+/* instrumentation build only (-DSGL_TOUCH_BITMAP): bytes (whole 32-byte DRAM sectors) of texture `handle` (0 = all textures)
+ * that samplers read since the last reset -- the measured B_tex of the roofline; the product library returns SGL_ERR_STATE */
+int sgl_debug_texel_touch(int handle, int reset, unsigned long long *bytes_out);
 int sgl_set_profiling(int on);
 int sgl_get_kernel_times(SglKernelTime *out, int capacity);   /* returns the number of entries written */
 

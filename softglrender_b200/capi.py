@@ -38,7 +38,7 @@ class SglDraw(C.Structure):
 class SglCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("passes", "draws", "primitives_in", "primitives_binned",
                                           "fragments_shaded", "samples_written", "kernel_launches", "clip_overflow",
-                                          "h2d_bytes", "d2h_bytes", "host_ns_pass_end", "host_ns_draw", "bin_spills")]
+                                          "h2d_bytes", "d2h_bytes", "host_ns_pass_end", "host_ns_draw", "bin_spills", "vertices_in", "indices_in")]
 
 
 class SglKernelTime(C.Structure):
@@ -49,7 +49,7 @@ class SglKernelTime(C.Structure):
 C_ABI_SYMBOLS = [
     "sgl_init", "sgl_shutdown", "sgl_last_error", "sgl_set_stream", "sgl_wait_idle", "sgl_get_counters",
     "sgl_reset_counters", "sgl_timer_begin", "sgl_timer_end", "sgl_set_profiling", "sgl_get_kernel_times",
-    "sgl_get_tile_list_sizes", "sgl_debug_tile_times", "sgl_debug_set_limits",
+    "sgl_get_tile_list_sizes", "sgl_debug_tile_times", "sgl_debug_set_limits", "sgl_debug_texel_touch",
     "sgl_shader_uniform_offset", "sgl_shader_sampler_slot",
     "sgl_shader_define_bit", "sgl_shader_uniform_size", "sgl_shader_varying_floats", "sgl_buffer_create",
     "sgl_buffer_upload", "sgl_buffer_destroy", "sgl_texture_create", "sgl_texture_destroy", "sgl_texture_upload",
@@ -115,6 +115,7 @@ def load():
     _lib.sgl_kat_depth.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     _lib.sgl_get_tile_list_sizes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib.sgl_debug_tile_times.argtypes = [C.c_int, C.c_void_p, C.c_int]
+    _lib.sgl_debug_texel_touch.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]
     _lib.sgl_debug_set_limits.argtypes = [C.c_longlong, C.c_longlong, C.c_longlong]
     _lib.sgl_get_kernel_times.argtypes = [C.POINTER(SglKernelTime), C.c_int]
     return _lib

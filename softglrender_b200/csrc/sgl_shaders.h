@@ -195,6 +195,9 @@ SGL_HD float sglShadowCalc(const SglFsCtx &c, V4 fragPos, V3 normal, V3 lightDir
         int iy = (int) floorf(xmul(proj.y + (float) y * po.y, (float) h));
         const int rx = sglWrapAxis(ix, w, sm.wrap), ry = sglWrapAxis(iy, h, sm.wrap);
         const bool border = rx == 1 || ry == 1, oob = (rx | ry) != 0;
+#if defined(SGL_TOUCH_BITMAP) && defined(__CUDA_ARCH__)
+        if (!(border || oob)) sglTouch(sm.tex->touch, sm.tex->base, base + (uint32_t) iy * (uint32_t) w + (uint32_t) ix);
+#endif
         const uint32_t t = SGL_LDG(base + (border || oob ? 0 : (uint32_t) iy * (uint32_t) w + (uint32_t) ix));
         tap[k] = border ? sm.border : (oob ? 0u : t);
       }

@@ -17,6 +17,26 @@
 #define SGL_LDG(p) (*(p))
 #endif
 
+// Instrumentation build (-DSGL_TOUCH_BITMAP, tools/gpu/texel_touch.py): every texel load of a sampler marks its 32-byte
+// DRAM sector in a per-texture bitmap -- the "touched-tile bitmap" SURVEY 8d asks for to measure the unique texel bytes a
+// frame needs (B_tex of the roofline).  Compiled out of the product library.
+#if defined(SGL_TOUCH_BITMAP) && defined(__CUDA_ARCH__)
+__device__ __forceinline__ void sglTouch(uint32_t *touch, const uint8_t *base, const void *addr) {
+  if (!touch) return;
+  const size_t sector = (size_t) ((const uint8_t *) addr - base) >> 5;
+  atomicOr(&touch[sector >> 5], 1u << (sector & 31));
+}
+#define SGL_TOUCH_FIELDS uint32_t *touch; const uint8_t *tbase;
+#define SGL_TOUCH_SET(view, t) (view).touch = (t)->touch; (view).tbase = (t)->base;
+#define SGL_TOUCH_NONE(view) (view).touch = nullptr; (view).tbase = nullptr;
+#define SGL_TOUCH(view, addr) sglTouch((view).touch, (view).tbase, (addr))
+#else
+#define SGL_TOUCH_FIELDS
+#define SGL_TOUCH_SET(view, t)
+#define SGL_TOUCH_NONE(view)
+#define SGL_TOUCH(view, addr)
+#endif
+
 SGL_HD uint32_t sglMorton2(uint32_t x, uint32_t y) {   // MortonBuffer::encode16_morton2, x in even bits
   uint32_t res = x | (y << 16);
   res = (res | (res << 4)) & 0x0f0f0f0fu;
@@ -83,6 +103,7 @@ SGL_HD bool sglWrapCoord(int &x, int &y, int w, int h, int wrap) {
 struct SglLevelView {
   const uint32_t *ptr;
   int w, h, layout;
+  SGL_TOUCH_FIELDS
 };
 SGL_HD SglLevelView sglLevelView(const SglTexObj *t, int layer, int level) {
   SglLevelView v;
@@ -90,12 +111,14 @@ SGL_HD SglLevelView sglLevelView(const SglTexObj *t, int layer, int level) {
   v.h = sglLevelDim(t->height, level);
   v.layout = t->layout;
   v.ptr = (const uint32_t *) (t->base + (size_t) layer * t->layerStride + t->levelOffset[level]);
+  SGL_TOUCH_SET(v, t)
   return v;
 }
 // texel at wrapped coordinates; rx/ry are the sglWrapAxis results of the two coordinates
 SGL_HD uint32_t sglFetchWrapped(const SglLevelView &lv, uint32_t border, int x, int rx, int y, int ry) {
   if (rx == 1 || ry == 1) return border;
   if ((rx | ry) != 0) return 0u;                       // Buffer::get bounds check -> T(0)
+  SGL_TOUCH(lv, lv.ptr + sglTexelIndex(lv.layout, lv.w, x, y));
   return SGL_LDG(lv.ptr + sglTexelIndex(lv.layout, lv.w, x, y));
 }
 
@@ -275,6 +298,7 @@ struct SglTapView {
   const uint32_t *ptr;   // level base
   int w, h;
   bool clamp;            // CLAMP_TO_EDGE, else REPEAT
+  SGL_TOUCH_FIELDS
 };
 struct SglTap {
   uint32_t s1, s2, s3, s4;
@@ -286,11 +310,13 @@ SGL_HD SglTapView sglTapView(const SglTexObj *t, int layer, int level, int wrap)
   v.h = sglLevelDim(t->height, level);
   v.ptr = (const uint32_t *) (t->base + (size_t) layer * t->layerStride + t->levelOffset[level]);
   v.clamp = wrap == SGL_WRAP_CLAMP_TO_EDGE;
+  SGL_TOUCH_SET(v, t)
   return v;
 }
 SGL_HD SglTapView sglTapViewDummy(const uint32_t *dummy) {
   SglTapView v;
   v.ptr = dummy; v.w = 1; v.h = 1; v.clamp = true;
+  SGL_TOUCH_NONE(v)
   return v;
 }
 SGL_HD int sglTapWrap(int x, int n, bool clamp) {
@@ -305,6 +331,10 @@ SGL_HD SglTap sglTapIssue(const SglTapView &t, float u, float v, int ox = 0, int
   int xa = sglTapWrap(x0, t.w, t.clamp), xb = sglTapWrap(x0 + 1, t.w, t.clamp);
   int ya = sglTapWrap(y0, t.h, t.clamp), yb = sglTapWrap(y0 + 1, t.h, t.clamp);
   SglTap r;
+  SGL_TOUCH(t, t.ptr + (uint32_t) ya * (uint32_t) t.w + (uint32_t) xa);
+  SGL_TOUCH(t, t.ptr + (uint32_t) ya * (uint32_t) t.w + (uint32_t) xb);
+  SGL_TOUCH(t, t.ptr + (uint32_t) yb * (uint32_t) t.w + (uint32_t) xa);
+  SGL_TOUCH(t, t.ptr + (uint32_t) yb * (uint32_t) t.w + (uint32_t) xb);
   r.s1 = SGL_LDG(t.ptr + (uint32_t) ya * (uint32_t) t.w + (uint32_t) xa);
   r.s2 = SGL_LDG(t.ptr + (uint32_t) ya * (uint32_t) t.w + (uint32_t) xb);
   r.s3 = SGL_LDG(t.ptr + (uint32_t) yb * (uint32_t) t.w + (uint32_t) xa);

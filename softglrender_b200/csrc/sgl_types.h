@@ -20,6 +20,9 @@ struct SglTexObj {
   unsigned long long levelOffset[SGL_MAX_LEVELS];  // bytes from the start of a layer
   unsigned long long layerStride;          // bytes
   int32_t width, height, levels, layers, format, samples, layout, pad;
+#ifdef SGL_TOUCH_BITMAP
+  uint32_t *touch;                         // instrumentation build: 1 bit per 32-byte sector of `base` that a sampler read
+#endif
 };
 
 // primitive kinds after assembly / polygon-mode expansion

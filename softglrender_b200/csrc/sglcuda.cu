@@ -116,7 +116,7 @@ struct Ctx {
   unsigned int *dOverflow = nullptr;   // device alias of hOverflow
   int clipScale = 1;                   // grows after an overflow: clip-vertex / fan arenas of later passes are this much larger
   long long binCapLimit = 0, clipMinVerts = 65536, clipMinFans = 32768;   // sgl_debug_set_limits (tests shrink them)
-  unsigned long long hostLaunches = 0, hostPasses = 0, hostDraws = 0, hostH2D = 0, hostD2H = 0, hostNsPassEnd = 0, hostNsDraw = 0;
+  unsigned long long hostLaunches = 0, hostPasses = 0, hostDraws = 0, hostH2D = 0, hostD2H = 0, hostNsPassEnd = 0, hostNsDraw = 0, hostVertices = 0, hostIndices = 0;
   cudaEvent_t evBegin = nullptr, evEnd = nullptr;
   std::string err;
 };
@@ -496,6 +496,8 @@ int sgl_get_counters(SglCounters *out) {
   out->host_ns_pass_end = g.hostNsPassEnd;
   out->host_ns_draw = g.hostNsDraw;
   out->bin_spills = c[1];
+  out->vertices_in = g.hostVertices;
+  out->indices_in = g.hostIndices;
   return checkOverflow();
 }
 
@@ -503,7 +505,7 @@ int sgl_reset_counters(void) {
   NEED_CTX();
   { int rc = syncAll(); if (rc) return rc; }
   CU(cudaMemset(g.dCounters, 0, 8 * sizeof(unsigned long long)));
-  g.hostLaunches = g.hostPasses = g.hostDraws = g.hostH2D = g.hostD2H = g.hostNsPassEnd = g.hostNsDraw = 0;
+  g.hostLaunches = g.hostPasses = g.hostDraws = g.hostH2D = g.hostD2H = g.hostNsPassEnd = g.hostNsDraw = g.hostVertices = g.hostIndices = 0;
   return SGL_OK;
 }
 
@@ -650,10 +652,41 @@ int sgl_texture_create(const SglTextureDesc *desc, int *handle_out) {
     CU(cudaMalloc(&o.resolve, (size_t) o.width * o.height * 4));
     CU(cudaMemsetAsync(o.resolve, 0, (size_t) o.width * o.height * 4, g.stream));
   }
+#ifdef SGL_TOUCH_BITMAP
+  {
+    const size_t words = t.bytes / 32 / 32 + 2;
+    CU(cudaMalloc(&t.obj.touch, words * 4));
+    CU(cudaMemsetAsync(t.obj.touch, 0, words * 4, g.stream));
+  }
+#endif
   g.textures.push_back(t);
   int h = (int) g.textures.size() - 1;
   *handle_out = h;
   return uploadTexObj(h);
+}
+
+// instrumentation build only (-DSGL_TOUCH_BITMAP): bytes of `handle` (whole 32-byte sectors) that samplers have read since
+// the last reset; handle 0 = sum over all textures.  The product library answers SGL_ERR_STATE.
+int sgl_debug_texel_touch(int handle, int reset, unsigned long long *bytes_out) {
+  NEED_CTX();
+#ifdef SGL_TOUCH_BITMAP
+  { int rc = syncAll(); if (rc) return rc; }
+  unsigned long long total = 0;
+  for (int h = 1; h < (int) g.textures.size(); h++) {
+    TextureRec &t = g.textures[h];
+    if (!t.alive || !t.obj.touch || (handle != 0 && handle != h)) continue;
+    const size_t words = t.bytes / 32 / 32 + 2;
+    std::vector<uint32_t> bits(words);
+    CU(cudaMemcpy(bits.data(), t.obj.touch, words * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t w : bits) total += (unsigned long long) __builtin_popcount(w) * 32ull;
+    if (reset) CU(cudaMemset(t.obj.touch, 0, words * 4));
+  }
+  if (bytes_out) *bytes_out = total;
+  return SGL_OK;
+#else
+  (void) handle; (void) reset; (void) bytes_out;
+  return fail(SGL_ERR_STATE, "sgl_debug_texel_touch needs the instrumentation build (python -m softglrender_b200.build --variant touch -DSGL_TOUCH_BITMAP)");
+#endif
 }
 
 int sgl_texture_destroy(int handle) {
@@ -664,6 +697,9 @@ int sgl_texture_destroy(int handle) {
   CU(cudaStreamSynchronize(g.copyStream));
   if (t->obj.base) CU(cudaFree(t->obj.base));
   if (t->obj.resolve) CU(cudaFree(t->obj.resolve));
+#ifdef SGL_TOUCH_BITMAP
+  if (t->obj.touch) CU(cudaFree(t->obj.touch));
+#endif
   if (t->rbDone) cudaEventDestroy(t->rbDone);
   *t = TextureRec();
   return SGL_OK;
@@ -981,6 +1017,8 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     oMask[i] = take((size_t) r.vertexCap * 4);
     oVout[i] = take((size_t) std::max(extraVerts, 1) * 64);
     oVary[i] = take((size_t) r.vertexCap * std::max(r.varyingStride, 1) * 4);
+    g.hostVertices += (unsigned long long) r.vertexCount;
+    g.hostIndices += (unsigned long long) r.indexCount;
     maxVerts = std::max(maxVerts, r.vertexCount);
     maxPrims = std::max(maxPrims, r.inputPrims);
     maxSlots = std::max(maxSlots, r.inputPrims * r.slotsPerPrim + r.appendCap);
