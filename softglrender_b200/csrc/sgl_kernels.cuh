@@ -94,7 +94,7 @@ struct SglDeviceAlloc {
       const uint32_t r = sglWarpAggregatedAdd(S.binReserved, (uint32_t) n);
       if (r + (uint32_t) n > S.binCapacity || r + (uint32_t) n < r) { big = true; atomicAdd(S.counters + 1, 1ull); }
     }
-    if (big) {
+    if (big) {   // sglBigBinKernel bins it (or leaves it in the residual list)
       uint32_t b = atomicAdd(S.bigCount, 1u);
       if (b < S.bigCapacity) S.bigList[b] = (uint32_t) slot;
       return true;
@@ -143,6 +143,63 @@ __global__ void __launch_bounds__(128) sglSetupKernel(const SglDrawRec *draws, S
   alloc.S = S;
   sglProcessInputPrim(d, blockIdx.y, i, hasDepth != 0, out, alloc);
   if (i == 0) atomicAdd(S.counters + 2, (unsigned long long) d.inputPrims);
+}
+
+// Binning of the big primitives (SglPassParams::bigAll): one CTA per big primitive (strided), threads over the tiles of
+// its pixel range, same conservative near-tile test as everywhere.  FILL = 0 (before the scan): reserves the exact number
+// of entries; if the bins cannot take them the primitive moves to the residual list (bigList) that every tile kernel
+// scans, else the per-tile counts are raised.  FILL = 1 (after the scan): writes the slots.  Residual primitives are
+// marked in bigAll by their top bit.
+template<int FILL>
+__global__ void __launch_bounds__(256) sglBigBinKernel(SglPassParams P) {
+  __shared__ uint32_t sWarp[8];
+  __shared__ uint32_t sOk;
+  uint32_t nBig = *P.bigAllCount;
+  if (nBig > P.bigCapacity) nBig = P.bigCapacity;
+  const int tid = threadIdx.x;
+  for (uint32_t i = blockIdx.x; i < nBig; i += gridDim.x) {
+    const uint32_t entry = P.bigAll[i];
+    if (FILL && (entry >> 31)) continue;
+    const uint32_t slot = entry & 0x7fffffffu;
+    const SglPrim p = P.prims[slot];
+    int tx0, ty0, tx1, ty1;
+    if (!sglPrimTiles(p, P.fbW, P.fbH, tx0, ty0, tx1, ty1)) continue;    // block-uniform
+    const int w = tx1 - tx0 + 1, n = w * (ty1 - ty0 + 1);
+    if (!FILL) {
+      uint32_t cnt = 0;
+      for (int k = tid; k < n; k += 256) {
+        const int tx = tx0 + k % w, ty = ty0 + k / w, t = ty * P.tilesX + tx;
+        if (P.tileOwner && P.tileOwner[t] != P.rank) continue;
+        if (sglPrimNearTile(p, tx, ty)) cnt++;
+      }
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      __syncthreads();
+      if ((tid & 31) == 0) sWarp[tid >> 5] = cnt;
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t total = 0;
+        for (int k = 0; k < 8; k++) total += sWarp[k];
+        const uint32_t r = atomicAdd(P.binReserved, total);
+        const bool ok = r + total <= P.binCapacity && r + total >= r;
+        if (!ok) {
+          P.bigAll[i] = entry | 0x80000000u;
+          const uint32_t b = atomicAdd(P.bigCount, 1u);
+          if (b < P.bigCapacity) P.bigList[b] = slot;
+          atomicAdd(P.counters + 1, 1ull);
+        }
+        sOk = ok ? 1u : 0u;
+      }
+      __syncthreads();
+      if (!sOk) continue;
+    }
+    for (int k = tid; k < n; k += 256) {
+      const int tx = tx0 + k % w, ty = ty0 + k / w, t = ty * P.tilesX + tx;
+      if (P.tileOwner && P.tileOwner[t] != P.rank) continue;
+      if (!sglPrimNearTile(p, tx, ty)) continue;
+      if (FILL) P.binSlots[P.tileOffset[t] + atomicAdd(&P.tileCursor[t], 1u)] = slot;
+      else atomicAdd(&P.tileCount[t], 1u);
+    }
+  }
 }
 
 // single CTA: tileOffset = exclusive scan(tileCount); tileOffset[nTiles] = total (clamped entries are dropped later)

@@ -8,7 +8,6 @@
 #define SGL_MAX_LEVELS 16
 #define SGL_OWNER_NONE 0xFFFFFFFFu
 #define SGL_BIG_PRIM_TILES 64       // primitives touching more tiles than this go to the pass-wide "big" list
-#define SGL_BIG_PER_TILE 32        // room per tile for big primitives in the pre-sorted tile lists
 #define SGL_TILE_UNSORTED 0xFFFFFFFFu
 #define SGL_TILE_CLASSES 4          // list length >= 192, >= 48, >= 12, rest
 #define SGL_RASTER_BLOCK 32         // RendererSoft::rasterBlockSize_ (RendererSoft.h:128)
@@ -99,6 +98,15 @@ struct __attribute__((aligned(16))) SglDrawRec {
   int32_t pad[2];
 };
 
+// One unit of work of the visibility kernel, written in heavy-first order by sglTileSortKernel (geometry stage)
+struct __attribute__((aligned(16))) SglVisWork {
+  uint32_t tile;        // 0xFFFFFFFF = nothing to do (quarters 1-3 of a heavy tile whose stream could not be prepared)
+  uint32_t streamOff;   // first entry of the tile's packed record stream (SglPassParams::stream)
+  uint32_t count;       // entries of the stream; SGL_TILE_UNSORTED = no stream: in-kernel gather / sort path
+  uint32_t quarter;     // 0..3: one 8x8 pixel quarter, one SAMPLE per lane (heavy MSAA tiles); 0xFFFFFFFF: whole tile
+};
+struct SglVisPrim;      // sgl_vis.cuh: primitive record + edge constants + slot, 128 bytes
+
 // pass-level parameters
 struct SglPassParams {
   // attachments
@@ -130,15 +138,26 @@ struct SglPassParams {
   uint32_t *tileCursor;         // [tiles]
   uint32_t *binSlots;           // primitive slots per tile (unordered)
   uint32_t binCapacity;
-  uint32_t *tileSorted;         // per tile: slots in submission order (bins + near big primitives), written by
-                                // sglTileSortKernel at tileOffset[t] + t * SGL_BIG_PER_TILE; null = not prepared
+  uint32_t *tileSorted;         // per tile: its bin in submission order, written by sglTileSortKernel at tileOffset[t];
+                                // null = not prepared
   uint32_t *tileSortedCount;    // [tiles] entries of the sorted list, SGL_TILE_UNSORTED = use the in-kernel gather
   uint32_t *tileOrder;          // [SGL_TILE_CLASSES][tiles]: tiles by descending list length class (heavy tiles are
   uint32_t *tileClassCount;     // [SGL_TILE_CLASSES]           launched first so that they cannot become stragglers)
   int32_t splitCap;             // MSAA visibility kernel: up to splitCap heavy tiles run as four quarter-tile CTAs
-  uint32_t *bigList;            // slots of big primitives
+  // big primitives (> SGL_BIG_PRIM_TILES tiles in their pixel range, or the bins were exhausted when they arrived): the
+  // setup kernel lists them in bigAll; sglBigBinKernel bins them tile by tile like everybody else.  Only what does not fit
+  // the bins then stays in the RESIDUAL list bigList/bigCount, which every tile kernel scans (normally empty).
+  uint32_t *bigAll;
+  uint32_t *bigAllCount;
+  uint32_t *bigList;
   uint32_t *bigCount;
-  uint32_t bigCapacity;
+  uint32_t bigCapacity;         // of both lists (>= primitive slots: they never overflow)
+  uint32_t *binReserved;        // running count of bin entries handed out
+  // visibility-kernel work list (one CTA per item) and the packed per-tile record streams it copies with cp.async.bulk
+  SglVisWork *work;
+  SglVisPrim *stream;
+  uint32_t *streamCursor;
+  uint32_t streamCapacity;      // entries
   const SglTexObj *textures;
   unsigned long long *counters; // device-side SglCounters mirror
   unsigned long long *tileTimes; // instrumentation (normally null): [tiles][2] globaltimer ns at CTA start / end of the visibility kernel

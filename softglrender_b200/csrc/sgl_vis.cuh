@@ -37,11 +37,30 @@ __device__ __forceinline__ bool sglPrimNearTile(const SglPrim &p, int tx, int ty
   return true;
 }
 
-struct __align__(16) SglVisPrim {   // shared-memory form of a primitive: record + per-triangle edge constants
+struct __align__(16) SglVisPrim {   // stream / shared-memory form of a primitive: record + per-triangle edge constants + slot
   SglPrim p;
   SglTriEdge e;
-  float pad[2];
+  uint32_t slot;
+  uint32_t pad;
 };
+static_assert(sizeof(SglVisPrim) == 128, "stream entries are 128 bytes (cp.async.bulk: 16-byte granules)");
+
+// ---- TMA-style bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier ----------------------------------
+__device__ __forceinline__ uint32_t sglSmemAddr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sglMbarInit(unsigned long long *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sglSmemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sglMbarExpectTx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sglSmemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sglBulkCopyG2S(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(sglSmemAddr(dst)), "l"(src), "r"(bytes), "r"(sglSmemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void sglMbarWait(unsigned long long *bar, uint32_t parity) {
+  asm volatile("{\n.reg .pred p;\nSGL_WAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra SGL_DONE_%=;\nbra SGL_WAIT_%=;\nSGL_DONE_%=:\n}"
+               ::"r"(sglSmemAddr(bar)), "r"(parity) : "memory");
+}
 
 __device__ __forceinline__ void sglBitonicSortKV(uint32_t *keys, uint32_t *vals, int n /* power of two */) {
   for (int k = 2; k <= n; k <<= 1) {
@@ -87,74 +106,117 @@ __device__ __forceinline__ void sglSortTileList(uint32_t *keys, uint32_t *vals, 
   sglBitonicSortKV(keys, vals, n2);
 }
 
-// Geometry-stage preparation of the tile lists: gathers a tile's bin plus the big primitives that can touch it, sorts by
-// order key and stores the slots, so that the pixel-stage kernels stream a ready list instead of running the gather /
-// sort latency chain with 256 mostly idle threads per tile.  Tiles whose list does not fit are flagged SGL_TILE_UNSORTED
-// and take the in-kernel path.  grid = tiles, block = 128.  (Compiled into the translation unit that launches it only.)
+// Geometry-stage preparation of the pixel stage's input: one WARP per tile (in heavy-first work order) sorts the tile's bin
+// by order key and writes (a) the sorted slots (tileSorted, read by the fused kernel), (b) the tile's packed record STREAM:
+// 128-byte entries {primitive record, edge constants, slot} in submission order, contiguous, so that the visibility kernel
+// fetches a whole batch with one cp.async.bulk, and (c) the work descriptor(s) of the tile.  Big primitives are in the bins
+// already (sglBigBinKernel).  Tiles whose list is longer than SGL_TILE_SORT_CAP or does not fit the stream, and every tile
+// while the residual big list is not empty, get SGL_TILE_UNSORTED and take the in-kernel path.
+// grid = ceil(tiles / 8), block = 256.  (Compiled into the translation unit that launches it only.)
 #ifdef SGL_WITH_TILE_SORT
 #define SGL_TILE_SORT_WARPS 8
 #define SGL_TILE_SORT_CAP 512     // longest list a warp sorts; longer ones are flagged SGL_TILE_UNSORTED
-// one WARP per heavy tile: grid = ceil(splitCap / 8), block = 256
+__device__ __forceinline__ void sglStreamStore(SglVisPrim *dst, const SglPrim *prims, uint32_t slot) {
+  SglVisPrim v;
+  const uint4 *src = reinterpret_cast<const uint4 *>(prims + slot);
+#pragma unroll
+  for (int q = 0; q < 4; q++) reinterpret_cast<uint4 *>(&v.p)[q] = __ldg(src + q);
+  if ((v.p.flags & SGL_PF_KIND_MASK) == SGL_PK_TRIANGLE) v.e = sglTriEdge(v.p);
+  else memset(&v.e, 0, sizeof(v.e));
+  v.slot = slot;
+  v.pad = 0;
+#pragma unroll
+  for (int q = 0; q < 8; q++) reinterpret_cast<uint4 *>(dst)[q] = reinterpret_cast<const uint4 *>(&v)[q];
+}
+
 __global__ void __launch_bounds__(32 * SGL_TILE_SORT_WARPS) sglTileSortKernel(SglPassParams P) {
   __shared__ uint32_t sKeys[SGL_TILE_SORT_WARPS][SGL_TILE_SORT_CAP];
   __shared__ uint32_t sSlots[SGL_TILE_SORT_WARPS][SGL_TILE_SORT_CAP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nTiles = P.tilesX * P.tilesY;
-  // only the heavy classes (0 and 1 of sglTileScanKernel) get a prepared list: they are the tiles the visibility kernel
-  // splits into quarter-tile CTAs; light tiles keep the in-kernel gather (thousands of them hide each other's latency)
-  const uint32_t h = (uint32_t) (blockIdx.x * SGL_TILE_SORT_WARPS + warp);
-  const uint32_t c0 = P.tileClassCount[0], c1 = P.tileClassCount[1];
-  if (h >= c0 + c1) return;
-  const int tile = (int) (h < c0 ? P.tileOrder[h] : P.tileOrder[(size_t) nTiles + (h - c0)]);
-  uint32_t *keys = sKeys[warp], *slots = sSlots[warp];
-  const int tx = tile % P.tilesX, ty = tile / P.tilesX;
+  const size_t nTiles = (size_t) P.tilesX * P.tilesY;
+  // work order: the class lists of sglTileScanKernel, heaviest class first
+  uint32_t cnt[SGL_TILE_CLASSES];
+#pragma unroll
+  for (int c = 0; c < SGL_TILE_CLASSES; c++) cnt[c] = P.tileClassCount[c];
+  const uint32_t owned = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+  const uint32_t o = (uint32_t) (blockIdx.x * SGL_TILE_SORT_WARPS + warp);
+  if (o >= owned) return;
+  const uint32_t heavyTiles = cnt[0] + cnt[1];
+  const uint32_t split = heavyTiles < (uint32_t) P.splitCap ? heavyTiles : (uint32_t) P.splitCap;   // splitCap = 0: no quarter items
+  const uint32_t ctaItems = 4u * split + (heavyTiles - split);
+  int tile = -1;
+  {
+    uint32_t b = o;
+#pragma unroll
+    for (int c = 0; c < SGL_TILE_CLASSES; c++) {
+      if (tile < 0 && b < cnt[c]) tile = (int) P.tileOrder[(size_t) c * nTiles + b];
+      if (tile < 0) b -= cnt[c];
+    }
+  }
   const uint32_t off = P.tileOffset[tile];
-  uint32_t nList = P.tileOffset[tile + 1] - off;
-  if (off + nList > P.binCapacity) nList = off < P.binCapacity ? P.binCapacity - off : 0;
-  uint32_t nBig = *P.bigCount;
-  if (nBig > P.bigCapacity) nBig = P.bigCapacity;
-  bool fits = nList <= SGL_TILE_SORT_CAP - SGL_BIG_PER_TILE;
-  int n = 0;
-  if (fits) {
-    for (uint32_t i = lane; i < nList; i += 32) {
-      const uint32_t slot = P.binSlots[off + i];
-      keys[i] = P.primKeys[slot];
-      slots[i] = slot;
-    }
-    n = (int) nList;
-    const int tx0 = tx * SGL_TILE, ty0 = ty * SGL_TILE, tx1 = tx0 + SGL_TILE - 1, ty1 = ty0 + SGL_TILE - 1;
-    int big = 0;
-    for (uint32_t i0 = 0; i0 < nBig; i0 += 32) {      // warp-uniform trip count
-      const uint32_t i = i0 + lane;
-      bool near = false;
-      uint32_t slot = 0;
-      if (i < nBig) {
-        slot = P.bigList[i];
-        const SglPrim &bp = P.prims[slot];
-        near = bp.bx0 <= tx1 && bp.bx1 >= tx0 && bp.by0 <= ty1 && bp.by1 >= ty0 && sglPrimNearTile(bp, tx, ty);
-      }
-      const uint32_t m = __ballot_sync(0xffffffffu, near);
-      const int pos = big + __popc(m & ((1u << lane) - 1u));
-      if (near && pos < SGL_BIG_PER_TILE) {
-        keys[n + pos] = P.primKeys[slot];
-        slots[n + pos] = slot;
-      }
-      big += __popc(m);
-    }
-    if (big > SGL_BIG_PER_TILE) fits = false;
-    n += big;
+  const uint32_t n = P.tileOffset[tile + 1] - off;
+  bool prepared = n <= SGL_TILE_SORT_CAP && *P.bigCount == 0;   // residual big primitives must be merged by key in-kernel
+  uint32_t streamOff = 0;
+  if (prepared && n > 0) {
+    if (lane == 0) streamOff = atomicAdd(P.streamCursor, n);
+    streamOff = __shfl_sync(0xffffffffu, streamOff, 0);
+    if (streamOff + n > P.streamCapacity || streamOff + n < streamOff) prepared = false;
   }
-  if (!fits) return;   // stays SGL_TILE_UNSORTED
-  __syncwarp();
-  // rank sort (keys are unique): each lane ranks its elements against the whole list, then scatters to global memory
-  uint32_t *dst = P.tileSorted + off + (size_t) tile * SGL_BIG_PER_TILE;
-  for (int i = lane; i < n; i += 32) {
-    const uint32_t k = keys[i];
-    int rank = 0;
-    for (int j = 0; j < n; j++) rank += keys[j] < k ? 1 : 0;
-    dst[rank] = slots[i];
+  if (prepared) {
+    uint32_t *dst = P.tileSorted + off;
+    SglVisPrim *sdst = P.stream + streamOff;
+    if (n <= 32) {
+      // the common case by far: one element per lane, rank by counting smaller keys across the warp
+      uint32_t slot = 0, key = 0xFFFFFFFFu;
+      if ((uint32_t) lane < n) {
+        slot = P.binSlots[off + lane];
+        key = P.primKeys[slot];
+      }
+      int rank = 0;
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const uint32_t kj = __shfl_sync(0xffffffffu, key, j);
+        rank += (kj < key) ? 1 : 0;
+      }
+      if ((uint32_t) lane < n) {
+        dst[rank] = slot;
+        sglStreamStore(sdst + rank, P.prims, slot);
+      }
+    } else {
+      uint32_t *keys = sKeys[warp], *slots = sSlots[warp];
+      for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t slot = P.binSlots[off + i];
+        keys[i] = P.primKeys[slot];
+        slots[i] = slot;
+      }
+      __syncwarp();
+      // rank sort (keys are unique): each lane ranks its elements against the whole list, then scatters to global memory
+      for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t k = keys[i];
+        int rank = 0;
+        for (uint32_t j = 0; j < n; j++) rank += keys[j] < k ? 1 : 0;
+        dst[rank] = slots[i];
+        sglStreamStore(sdst + rank, P.prims, slots[i]);
+      }
+    }
+    if (lane == 0) P.tileSortedCount[tile] = n;
   }
-  if (lane == 0) P.tileSortedCount[tile] = (uint32_t) n;
+  // work descriptors (sglVisWorkCounts): split heavy tiles = four quarter items, other heavy tiles = one CTA item, light
+  // tiles = one warp item each
+  const uint32_t none = 0xFFFFFFFFu;
+  if (o < split) {
+    if (lane < 4) {
+      SglVisWork w;
+      if (prepared) { w.tile = (uint32_t) tile; w.streamOff = streamOff; w.count = n; w.quarter = (uint32_t) lane; }
+      else if (lane == 0) { w.tile = (uint32_t) tile; w.streamOff = 0; w.count = SGL_TILE_UNSORTED; w.quarter = none; }
+      else { w.tile = none; w.streamOff = 0; w.count = 0; w.quarter = none; }
+      P.work[4u * o + lane] = w;
+    }
+  } else if (lane == 0) {
+    SglVisWork w;
+    w.tile = (uint32_t) tile; w.streamOff = streamOff; w.count = prepared ? n : SGL_TILE_UNSORTED; w.quarter = none;
+    P.work[o < heavyTiles ? 4u * split + (o - split) : ctaItems + (o - heavyTiles)] = w;
+  }
 }
 #endif  // SGL_WITH_TILE_SORT
 
@@ -291,242 +353,242 @@ __device__ __forceinline__ void sglVisPixelPrim(const SglPassParams &P, const Sg
   }
 }
 
+// Number of work items that need a whole CTA (tiles of the two heavy classes: four quarter items each while they fit
+// splitCap, one whole-tile item each beyond it); the items after them are light tiles (< 40 primitives) that ONE WARP
+// rasterises on its own.  Same arithmetic in sglTileSortKernel (writer) and sglVisKernel (reader).
+__device__ __forceinline__ void sglVisWorkCounts(const SglPassParams &P, uint32_t &ctaItems, uint32_t &allItems, uint32_t &heavy, uint32_t &split) {
+  uint32_t cnt[SGL_TILE_CLASSES];
+#pragma unroll
+  for (int c = 0; c < SGL_TILE_CLASSES; c++) cnt[c] = P.tileClassCount[c];
+  heavy = cnt[0] + cnt[1];
+  split = heavy < (uint32_t) P.splitCap ? heavy : (uint32_t) P.splitCap;
+  ctaItems = 4u * split + (heavy - split);
+  allItems = ctaItems + cnt[2] + cnt[3];
+}
+
+// Visibility kernel: one CTA per work item of the heavy-first list the geometry stage prepared (a whole tile, or -- heavy
+// MSAA tiles -- an 8x8 quarter with one sample per lane).  The CTA reads its 16-byte descriptor, then streams the item's
+// packed records in batches of 64 through a double-buffered shared-memory ring: thread 0 issues the cp.async.bulk of batch
+// b + 1 onto an mbarrier while all eight warps rasterise batch b.  Descriptor -> records is the whole dependent-load chain
+// of a tile (it used to be class counts -> tile order -> offsets -> slots -> keys -> records, with a sort in between).
+// Tiles without a prepared stream (SGL_TILE_UNSORTED: list longer than the sort cap, stream region full, residual big
+// primitives) take the in-kernel gather / sort path.
 template<int NS>
 __global__ void __launch_bounds__(SGL_TILE_THREADS, SGL_VIS_MIN_BLOCKS) sglVisKernel(SglPassParams P) {
-  __shared__ uint32_t sKeys[SGL_SORT_CAP];
+  constexpr int kRingBytes = 2 * SGL_VIS_BATCH * (int) sizeof(SglVisPrim);
+  __shared__ __align__(128) unsigned char sPool[kRingBytes];
+  SglVisPrim (*sRec)[SGL_VIS_BATCH] = reinterpret_cast<SglVisPrim (*)[SGL_VIS_BATCH]>(sPool);
+  __shared__ uint32_t sKeys[SGL_SORT_CAP];      // in-kernel path only
   __shared__ uint32_t sSlots[SGL_SORT_CAP];
-  __shared__ SglVisPrim sPrims[SGL_VIS_BATCH];
+  __shared__ __align__(8) unsigned long long sBar[2];
   __shared__ int sCount;
 
-  int quarter;
-  const int tile = sglTileOfBlock(P, blockIdx.x, NS == 4 ? P.splitCap : 0, quarter);
-  if (tile < 0) return;
-  const int tx = tile % P.tilesX, ty = tile / P.tilesX;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (P.tileTimes && tid == 0 && quarter <= 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    P.tileTimes[2 * tile] = t;
-  }
-  if (NS == 4 && quarter >= 0) {
-    const uint32_t pre = P.tileSortedCount[tile];
-    if (pre == SGL_TILE_UNSORTED) {
-      if (quarter != 0) return;       // list not prepared: quarter 0 takes the whole tile below
-    } else {
-      // ---- heavy tile, one 8x8 pixel quarter per CTA, one SAMPLE per lane: a warp owns a 4x2 pixel block
-      const int wbx = tx * SGL_TILE + (quarter & 1) * 8 + (warp & 1) * 4, wby = ty * SGL_TILE + (quarter >> 1) * 8 + (warp >> 1) * 2;
-      const int px = wbx + ((lane >> 2) & 3), py = wby + (lane >> 4), smp = lane & 3;
-      const bool inFb = px < P.fbW && py < P.fbH;
-      const bool hasColor = P.colorBase != nullptr, hasDepth = P.depthBase != nullptr;
-      const size_t idx = ((size_t) py * P.fbW + px) * 4 + smp;
-      float depth = P.clearDepth;
-      uint32_t owner = SGL_OWNER_NONE;
-      if (inFb && hasDepth && !P.clearDepthFlag) depth = P.depthBase[idx];
-      const uint32_t *list = P.tileSorted + P.tileOffset[tile] + (size_t) tile * SGL_BIG_PER_TILE;
-      for (uint32_t b0 = 0; b0 < pre; b0 += SGL_VIS_BATCH) {
-        const int nb = pre - b0 < SGL_VIS_BATCH ? (int) (pre - b0) : SGL_VIS_BATCH;
-        __syncthreads();
-        {
-          const int r = tid >> 2, q = tid & 3;
-          if (r < nb) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(P.prims + __ldg(list + b0 + r));
-            reinterpret_cast<uint4 *>(&sPrims[r].p)[q] = __ldg(src + q);
-          }
-          if (tid < nb) sSlots[tid] = __ldg(list + b0 + tid);
-        }
-        __syncthreads();
-        if (tid < nb && (sPrims[tid].p.flags & SGL_PF_KIND_MASK) == SGL_PK_TRIANGLE) sPrims[tid].e = sglTriEdge(sPrims[tid].p);
-        __syncthreads();
-        uint32_t rel[2];
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-          const int i = hh * 32 + lane;
-          bool r = false;
-          if (i < nb) {
-            const SglVisPrim &vp = sPrims[i];
-            r = vp.p.bx0 <= wbx + 3 && vp.p.bx1 >= wbx && vp.p.by0 <= wby + 1 && vp.p.by1 >= wby;
-            if (r) {
-              const uint32_t kind = vp.p.flags & SGL_PF_KIND_MASK;
-              if (kind == SGL_PK_TRIANGLE) r = !sglTriSurelyOutside(vp.e, (float) wbx + 2.f, (float) wby + 1.f, 1.875f, 0.875f);
-              else if (kind == SGL_PK_LINE) r = sglLineNearRect(vp.p, wbx, wby, wbx + 3, wby + 1);
-            }
-          }
-          rel[hh] = __ballot_sync(0xffffffffu, r);
-        }
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-          uint32_t m = rel[hh];
-          while (m) {
-            const int k = hh * 32 + __ffs(m) - 1;
-            m &= m - 1;
-            sglVisSamplePrim(P, sPrims[k], sSlots[k], px, py, smp, lane, inFb, depth, owner, hasColor, hasDepth);
-          }
-        }
-      }
-      if (inFb) {
-        if (hasDepth) P.depthBase[idx] = depth;
-        if (hasColor) P.vis[idx] = owner;
-      }
-      if (P.tileTimes) {
-        __syncthreads();
-        if (tid == 0 && quarter == 0) {
-          unsigned long long t;
-          asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-          P.tileTimes[2 * tile + 1] = t;
-        }
-      }
-      return;
+  const SglVisWork wk = P.work[blockIdx.x];     // in bounds for every CTA of the grid; valid iff blockIdx.x < allItems
+  uint32_t ctaItems, allItems, heavyTiles, splitTiles;
+  sglVisWorkCounts(P, ctaItems, allItems, heavyTiles, splitTiles);
+  if (blockIdx.x >= allItems) return;
+  if (wk.tile == 0xFFFFFFFFu) return;
+  const int tile = (int) wk.tile;
+  const bool streamed = wk.count != SGL_TILE_UNSORTED;
+  const uint32_t count = streamed ? wk.count : 0u;
+  if (tid == 0 && streamed && count > 0) {   // first two batches in flight before anything else
+    sglMbarInit(&sBar[0], 1);
+    sglMbarInit(&sBar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t n0 = count < SGL_VIS_BATCH ? count : SGL_VIS_BATCH;
+    sglMbarExpectTx(&sBar[0], n0 * (uint32_t) sizeof(SglVisPrim));
+    sglBulkCopyG2S(&sRec[0][0], P.stream + wk.streamOff, n0 * (uint32_t) sizeof(SglVisPrim), &sBar[0]);
+    if (count > SGL_VIS_BATCH) {
+      const uint32_t n1 = count - SGL_VIS_BATCH < SGL_VIS_BATCH ? count - SGL_VIS_BATCH : SGL_VIS_BATCH;
+      sglMbarExpectTx(&sBar[1], n1 * (uint32_t) sizeof(SglVisPrim));
+      sglBulkCopyG2S(&sRec[1][0], P.stream + wk.streamOff + SGL_VIS_BATCH, n1 * (uint32_t) sizeof(SglVisPrim), &sBar[1]);
     }
   }
-  // a warp owns an 8x4 pixel block of the tile (same mapping as the shading kernel): small triangles then concern one
-  // or two warps of the CTA instead of most 16x2 strips
-  const int wbx = tx * SGL_TILE + (warp & 1) * 8, wby = ty * SGL_TILE + (warp >> 1) * 4;
-  const int px = wbx + (lane & 7);
-  const int py = wby + (lane >> 3);
-  const bool inFb = px < P.fbW && py < P.fbH;
   const bool hasColor = P.colorBase != nullptr, hasDepth = P.depthBase != nullptr;
-  const size_t pix = (size_t) py * P.fbW + px;
+  const int tx = tile % P.tilesX, ty = tile / P.tilesX;
 
+  // ---- pixel state (registers): one pixel per lane (a warp owns an 8x4 block), or -- quarter items -- one sample per
+  //      lane (a warp owns a 4x2 block, depth[0] / owner[0] only)
+  const bool quarterMode = NS == 4 && wk.quarter != 0xFFFFFFFFu;
+  int wbx, wby, px, py, smp = 0;
+  if (quarterMode) {
+    wbx = tx * SGL_TILE + (int) (wk.quarter & 1u) * 8 + (warp & 1) * 4;
+    wby = ty * SGL_TILE + (int) (wk.quarter >> 1) * 8 + (warp >> 1) * 2;
+    px = wbx + ((lane >> 2) & 3);
+    py = wby + (lane >> 4);
+    smp = lane & 3;
+  } else {
+    wbx = tx * SGL_TILE + (warp & 1) * 8;
+    wby = ty * SGL_TILE + (warp >> 1) * 4;
+    px = wbx + (lane & 7);
+    py = wby + (lane >> 3);
+  }
+  const bool inFb = px < P.fbW && py < P.fbH;
+  const size_t pix = (size_t) py * P.fbW + px;
   float depth[NS];
   uint32_t owner[NS];
 #pragma unroll
   for (int s = 0; s < NS; s++) { depth[s] = P.clearDepth; owner[s] = SGL_OWNER_NONE; }
   if (inFb && hasDepth && !P.clearDepthFlag) {
-    if (NS == 4) {
+    if (quarterMode) depth[0] = P.depthBase[pix * 4 + smp];
+    else if (NS == 4) {
       float4 dq = reinterpret_cast<const float4 *>(P.depthBase)[pix];
       depth[0] = dq.x; depth[NS > 1 ? 1 : 0] = dq.y; depth[NS > 2 ? 2 : 0] = dq.z; depth[NS > 3 ? 3 : 0] = dq.w;
     } else depth[0] = P.depthBase[pix];
   }
+  const bool stampIt = P.tileTimes && tid == 0 && (!quarterMode || wk.quarter == 0);
+  if (stampIt) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    P.tileTimes[2 * tile] = t;
+  }
 
-  const uint32_t off = P.tileOffset[tile];
-
-  // one batch of <= SGL_VIS_BATCH records whose slots sit in slots[0..nb): stage the records in shared memory, derive the
-  // edge constants, cull per warp, then every pixel visits the survivors in order
-  auto runBatch = [&](const uint32_t *slots, int nb) {
-    {  // 64 records x 4 x uint4 = one 16-byte load per thread, then one thread per record derives the edge constants
-      const int r = tid >> 2, q = tid & 3;
-      if (r < nb) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(P.prims + slots[r]);
-        reinterpret_cast<uint4 *>(&sPrims[r].p)[q] = __ldg(src + q);
-      }
-    }
-    __syncthreads();
-    if (tid < nb && (sPrims[tid].p.flags & SGL_PF_KIND_MASK) == SGL_PK_TRIANGLE) sPrims[tid].e = sglTriEdge(sPrims[tid].p);
-    __syncthreads();
-    // warp-level cull: each lane tests two records of the batch against the warp's 8x4 block (bbox, then the same
-    // conservative outside test the pixels use, over the block's sample positions); the warp then visits only the
-    // surviving records, in order
+  // cull one staged batch (<= 64 records) against the warp's pixel block, then every pixel (sample) visits the survivors
+  auto processBatch = [&](const SglVisPrim *recs, int n) {
     uint32_t rel[2];
 #pragma unroll
     for (int hh = 0; hh < 2; hh++) {
       const int idx = hh * 32 + lane;
       bool r = false;
-      if (idx < nb) {
-        const SglVisPrim &vp = sPrims[idx];
-        r = vp.p.bx0 <= wbx + 7 && vp.p.bx1 >= wbx && vp.p.by0 <= wby + 3 && vp.p.by1 >= wby;
-        if (r) {
-          const uint32_t kind = vp.p.flags & SGL_PF_KIND_MASK;
-          if (kind == SGL_PK_TRIANGLE) r = !sglTriSurelyOutside(vp.e, (float) wbx + 4.f, (float) wby + 2.f, 3.875f, 1.875f);
-          else if (kind == SGL_PK_LINE) r = sglLineNearRect(vp.p, wbx, wby, wbx + 7, wby + 3);
+      if (idx < n) {
+        const SglVisPrim &vp = recs[idx];
+        const uint32_t kind = vp.p.flags & SGL_PF_KIND_MASK;
+        if (quarterMode) {
+          r = vp.p.bx0 <= wbx + 3 && vp.p.bx1 >= wbx && vp.p.by0 <= wby + 1 && vp.p.by1 >= wby;
+          if (r) {
+            if (kind == SGL_PK_TRIANGLE) r = !sglTriSurelyOutside(vp.e, (float) wbx + 2.f, (float) wby + 1.f, 1.875f, 0.875f);
+            else if (kind == SGL_PK_LINE) r = sglLineNearRect(vp.p, wbx, wby, wbx + 3, wby + 1);
+          }
+        } else {
+          r = vp.p.bx0 <= wbx + 7 && vp.p.bx1 >= wbx && vp.p.by0 <= wby + 3 && vp.p.by1 >= wby;
+          if (r) {
+            if (kind == SGL_PK_TRIANGLE) r = !sglTriSurelyOutside(vp.e, (float) wbx + 4.f, (float) wby + 2.f, 3.875f, 1.875f);
+            else if (kind == SGL_PK_LINE) r = sglLineNearRect(vp.p, wbx, wby, wbx + 7, wby + 3);
+          }
         }
       }
       rel[hh] = __ballot_sync(0xffffffffu, r);
     }
-    if (inFb) {
 #pragma unroll
-      for (int hh = 0; hh < 2; hh++) {
-        uint32_t m = rel[hh];
-        while (m) {
-          const int k = hh * 32 + __ffs(m) - 1;
-          m &= m - 1;
-          sglVisPixelPrim<NS>(P, sPrims[k], slots[k], px, py, depth, owner, hasColor, hasDepth);
-        }
+    for (int hh = 0; hh < 2; hh++) {
+      uint32_t m = rel[hh];
+      while (m) {
+        const int k = hh * 32 + __ffs(m) - 1;
+        m &= m - 1;
+        if (NS == 4 && quarterMode) sglVisSamplePrim(P, recs[k], recs[k].slot, px, py, smp, lane, inFb, depth[0], owner[0], hasColor, hasDepth);
+        else if (inFb) sglVisPixelPrim<NS>(P, recs[k], recs[k].slot, px, py, depth, owner, hasColor, hasDepth);
       }
     }
   };
 
-  const uint32_t pre = P.tileSortedCount ? P.tileSortedCount[tile] : SGL_TILE_UNSORTED;
-  if (pre != SGL_TILE_UNSORTED) {
-    // list prepared by sglTileSortKernel: stream it
-    const uint32_t *list = P.tileSorted + off + (size_t) tile * SGL_BIG_PER_TILE;
-    for (uint32_t b0 = 0; b0 < pre; b0 += SGL_VIS_BATCH) {
-      const int nb = pre - b0 < SGL_VIS_BATCH ? (int) (pre - b0) : SGL_VIS_BATCH;
-      __syncthreads();
-      if (tid < nb) sSlots[tid] = __ldg(list + b0 + tid);
-      __syncthreads();
-      runBatch(sSlots, nb);
+  if (streamed) {
+    uint32_t phase0 = 0, phase1 = 0;
+    if (count > 0) __syncthreads();     // thread 0's mbarrier initialisation is visible before anybody waits on them
+    for (uint32_t b0 = 0, u = 0; b0 < count; b0 += SGL_VIS_BATCH, u++) {
+      const int slot = (int) (u & 1u);
+      const int nb = count - b0 < SGL_VIS_BATCH ? (int) (count - b0) : SGL_VIS_BATCH;
+      if (slot == 0) { sglMbarWait(&sBar[0], phase0); phase0 ^= 1u; }
+      else { sglMbarWait(&sBar[1], phase1); phase1 ^= 1u; }
+      processBatch(&sRec[slot][0], nb);
+      const uint32_t b2 = b0 + 2 * SGL_VIS_BATCH;      // this ring slot's next batch
+      if (b2 < count) {
+        __syncthreads();                               // everybody is done reading the slot
+        if (tid == 0) {
+          const uint32_t n2 = count - b2 < SGL_VIS_BATCH ? count - b2 : SGL_VIS_BATCH;
+          sglMbarExpectTx(&sBar[slot], n2 * (uint32_t) sizeof(SglVisPrim));
+          sglBulkCopyG2S(&sRec[slot][0], P.stream + wk.streamOff + b2, n2 * (uint32_t) sizeof(SglVisPrim), &sBar[slot]);
+        }
+      }
     }
   } else {
-  uint32_t nList = P.tileOffset[tile + 1] - off;
-  if (off + nList > P.binCapacity) nList = off < P.binCapacity ? P.binCapacity - off : 0;
-  uint32_t nBig = *P.bigCount;
-  if (nBig > P.bigCapacity) nBig = P.bigCapacity;
-  const int tx0 = tx * SGL_TILE, ty0 = ty * SGL_TILE, tx1 = tx0 + SGL_TILE - 1, ty1 = ty0 + SGL_TILE - 1;
-  // key windows: the common case (everything fits) is one window covering all keys
-  uint32_t lo = 0;
-  const uint32_t keyEnd = 0xFFFFFFFFu;
-  const bool fits = (nList + nBig) <= SGL_SORT_CAP;
-  while (true) {
-    uint32_t hi = keyEnd;
-    while (true) {   // gather candidates with lo <= key < hi
-      if (tid == 0) sCount = 0;
-      __syncthreads();
-      for (uint32_t i = tid; i < nList; i += SGL_TILE_THREADS) {
-        uint32_t slot = P.binSlots[off + i];
-        uint32_t key = P.primKeys[slot];
-        if (key >= lo && key < hi) {
-          int idx = atomicAdd(&sCount, 1);
-          if (idx < SGL_SORT_CAP) { sKeys[idx] = key; sSlots[idx] = slot; }
-        }
-      }
-      for (uint32_t i = tid; i < nBig; i += SGL_TILE_THREADS) {
-        uint32_t slot = P.bigList[i];
-        uint32_t key = P.primKeys[slot];
-        if (key >= lo && key < hi) {
-          const SglPrim &bp = P.prims[slot];
-          if (bp.bx0 <= tx1 && bp.bx1 >= tx0 && bp.by0 <= ty1 && bp.by1 >= ty0 && sglPrimNearTile(bp, tx, ty)) {
+    // ---- in-kernel path: gather the tile's bin and the residual big primitives in key windows, sort, stage, process
+    SglVisPrim *stage = &sRec[0][0];
+    const uint32_t off = P.tileOffset[tile];
+    uint32_t nList = P.tileOffset[tile + 1] - off;
+    if (off + nList > P.binCapacity) nList = off < P.binCapacity ? P.binCapacity - off : 0;
+    uint32_t nBig = *P.bigCount;
+    if (nBig > P.bigCapacity) nBig = P.bigCapacity;
+    const int tx0 = tx * SGL_TILE, ty0 = ty * SGL_TILE, tx1 = tx0 + SGL_TILE - 1, ty1 = ty0 + SGL_TILE - 1;
+    uint32_t lo = 0;
+    const uint32_t keyEnd = 0xFFFFFFFFu;
+    const bool fits = (nList + nBig) <= SGL_SORT_CAP;
+    while (true) {
+      uint32_t hi = keyEnd;
+      while (true) {   // gather candidates with lo <= key < hi
+        if (tid == 0) sCount = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < nList; i += SGL_TILE_THREADS) {
+          uint32_t s2 = P.binSlots[off + i];
+          uint32_t key = P.primKeys[s2];
+          if (key >= lo && key < hi) {
             int idx = atomicAdd(&sCount, 1);
-            if (idx < SGL_SORT_CAP) { sKeys[idx] = key; sSlots[idx] = slot; }
+            if (idx < SGL_SORT_CAP) { sKeys[idx] = key; sSlots[idx] = s2; }
           }
         }
+        for (uint32_t i = tid; i < nBig; i += SGL_TILE_THREADS) {
+          uint32_t s2 = P.bigList[i];
+          uint32_t key = P.primKeys[s2];
+          if (key >= lo && key < hi) {
+            const SglPrim &bp = P.prims[s2];
+            if (bp.bx0 <= tx1 && bp.bx1 >= tx0 && bp.by0 <= ty1 && bp.by1 >= ty0 && sglPrimNearTile(bp, tx, ty)) {
+              int idx = atomicAdd(&sCount, 1);
+              if (idx < SGL_SORT_CAP) { sKeys[idx] = key; sSlots[idx] = s2; }
+            }
+          }
+        }
+        __syncthreads();
+        if (sCount <= SGL_SORT_CAP) break;
+        hi = lo + (hi - lo) / 2;          // too many: halve the key window and retry
+        __syncthreads();
+      }
+      const int n = sCount;
+      sglSortTileList(sKeys, sSlots, n);
+      for (int b0 = 0; b0 < n; b0 += SGL_VIS_BATCH) {   // process in order
+        const int nbb = n - b0 < SGL_VIS_BATCH ? n - b0 : SGL_VIS_BATCH;
+        __syncthreads();
+        {  // 64 records x 4 x uint4 = one 16-byte load per thread, then one thread per record derives the edge constants
+          const int r = tid >> 2, q = tid & 3;
+          if (r < nbb) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(P.prims + sSlots[b0 + r]);
+            reinterpret_cast<uint4 *>(&stage[r].p)[q] = __ldg(src + q);
+          }
+        }
+        __syncthreads();
+        if (tid < nbb) {
+          if ((stage[tid].p.flags & SGL_PF_KIND_MASK) == SGL_PK_TRIANGLE) stage[tid].e = sglTriEdge(stage[tid].p);
+          stage[tid].slot = sSlots[b0 + tid];
+        }
+        __syncthreads();
+        processBatch(stage, nbb);
       }
       __syncthreads();
-      if (sCount <= SGL_SORT_CAP) break;
-      hi = lo + (hi - lo) / 2;          // too many: halve the key window and retry
-      __syncthreads();
+      if (fits || hi == keyEnd) break;
+      lo = hi;
     }
-    const int n = sCount;
-    sglSortTileList(sKeys, sSlots, n);
-    for (int b0 = 0; b0 < n; b0 += SGL_VIS_BATCH) {   // process in order
-      const int nb = n - b0 < SGL_VIS_BATCH ? n - b0 : SGL_VIS_BATCH;
-      __syncthreads();
-      runBatch(sSlots + b0, nb);
-    }
-    __syncthreads();
-    if (fits || hi == keyEnd) break;
-    lo = hi;
-  }
   }
 
   if (inFb) {
-    if (hasDepth) {
-      if (NS == 4) reinterpret_cast<float4 *>(P.depthBase)[pix] =
-          make_float4(depth[0], depth[NS > 1 ? 1 : 0], depth[NS > 2 ? 2 : 0], depth[NS > 3 ? 3 : 0]);
-      else P.depthBase[pix] = depth[0];
-    }
-    if (hasColor) {
-      if (NS == 4) reinterpret_cast<uint4 *>(P.vis)[pix] =
-          make_uint4(owner[0], owner[NS > 1 ? 1 : 0], owner[NS > 2 ? 2 : 0], owner[NS > 3 ? 3 : 0]);
-      else P.vis[pix] = owner[0];
+    if (quarterMode) {
+      if (hasDepth) P.depthBase[pix * 4 + smp] = depth[0];
+      if (hasColor) P.vis[pix * 4 + smp] = owner[0];
+    } else {
+      if (hasDepth) {
+        if (NS == 4) reinterpret_cast<float4 *>(P.depthBase)[pix] =
+            make_float4(depth[0], depth[NS > 1 ? 1 : 0], depth[NS > 2 ? 2 : 0], depth[NS > 3 ? 3 : 0]);
+        else P.depthBase[pix] = depth[0];
+      }
+      if (hasColor) {
+        if (NS == 4) reinterpret_cast<uint4 *>(P.vis)[pix] =
+            make_uint4(owner[0], owner[NS > 1 ? 1 : 0], owner[NS > 2 ? 2 : 0], owner[NS > 3 ? 3 : 0]);
+        else P.vis[pix] = owner[0];
+      }
     }
   }
-  if (P.tileTimes) {
-    __syncthreads();
-    if (tid == 0) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-      P.tileTimes[2 * tile + 1] = t;
-    }
+  if (stampIt) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    P.tileTimes[2 * tile + 1] = t;
   }
 }
 

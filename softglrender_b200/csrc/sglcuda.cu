@@ -983,7 +983,9 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   size_t oZero = off;
   size_t oDrawCounters = take(sizeof(int32_t) * 2 * std::max(nDraws, 1));
   size_t oBigCount = take(sizeof(uint32_t));
+  size_t oBigAllCount = take(sizeof(uint32_t));
   size_t oBinReserved = take(sizeof(uint32_t));
+  size_t oStreamCursor = take(sizeof(uint32_t));
   size_t oTileCount = take(sizeof(uint32_t) * nTiles);
   size_t oTileCursor = take(sizeof(uint32_t) * nTiles);
   size_t oTileClassCount = take(sizeof(uint32_t) * SGL_TILE_CLASSES);
@@ -1028,15 +1030,21 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   size_t oPrimVerts = take(sizeof(SglPrimVerts) * std::max(primSlots, 1));
   size_t oPrimKeys = take(sizeof(uint32_t) * std::max(primSlots, 1));
   size_t oBigList = take(sizeof(uint32_t) * std::max(primSlots, 1));
+  size_t oBigAll = take(sizeof(uint32_t) * std::max(primSlots, 1));
   size_t binCapacity = std::min<size_t>(std::max<size_t>((size_t) primSlots * 8, 1 << 20), (size_t) 1 << 29);
   if (g.binCapLimit > 0) binCapacity = std::min<size_t>(binCapacity, (size_t) g.binCapLimit);
   // depth-only path: the region holds 64-byte work items instead (>= 2 per primitive slot + one per 512 framebuffer pixels)
   if (depthOnly) binCapacity = ((size_t) primSlots * 2 + (size_t) fbW * fbH / 512 + 65536) * (sizeof(SglPrim) / sizeof(uint32_t));
   size_t oBins = take(sizeof(uint32_t) * binCapacity);
-  // pre-sorted tile lists (sglTileSortKernel): bins + room for SGL_BIG_PER_TILE big primitives per tile
-  size_t oTileSorted = depthOnly ? 0 : take(sizeof(uint32_t) * (binCapacity + (size_t) nTiles * SGL_BIG_PER_TILE));
+  // pre-sorted tile lists (sglTileSortKernel)
+  size_t oTileSorted = depthOnly ? 0 : take(sizeof(uint32_t) * binCapacity);
   size_t oTileSortedCount = depthOnly ? 0 : take(sizeof(uint32_t) * nTiles);
   size_t oTileOrder = depthOnly ? 0 : take(sizeof(uint32_t) * nTiles * SGL_TILE_CLASSES);
+  // visibility-kernel work items (heavy MSAA tiles: four quarter items) and the packed per-tile record streams
+  const int splitCap = (!depthOnly && samples == 4 && !g.noSplit) ? std::max(nTiles / 4, 1) : 0;
+  const size_t streamCapacity = depthOnly ? 0 : std::min<size_t>((size_t) 2 * std::max(primSlots, 1) + (size_t) 16 * nTiles, binCapacity);
+  size_t oWork = depthOnly ? 0 : take(sizeof(SglVisWork) * ((size_t) nTiles + 3 * (size_t) splitCap));
+  size_t oStream = depthOnly ? 0 : take((size_t) 128 * std::max<size_t>(streamCapacity, 1));
   Ctx::Arena &arena = g.arenas[g.arenaNext];
   const cudaStream_t geomStream = g.geomStreams[g.arenaNext];
   g.arenaNext = (g.arenaNext + 1) % 3;
@@ -1122,13 +1130,20 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   if (!depthOnly) { g.lastTileSortedCount = (const uint32_t *) (A + oTileSortedCount); g.lastTilesX = tilesX; g.lastTilesY = tilesY; }
   P.tileOrder = depthOnly ? nullptr : (uint32_t *) (A + oTileOrder);
   P.tileClassCount = (uint32_t *) (A + oTileClassCount);
-  P.splitCap = (!depthOnly && samples == 4 && !g.noSplit) ? std::max(nTiles / 4, 1) : 0;
+  P.splitCap = splitCap;
+  P.work = depthOnly ? nullptr : (SglVisWork *) (A + oWork);
+  P.stream = depthOnly ? nullptr : (SglVisPrim *) (A + oStream);
+  P.streamCursor = (uint32_t *) (A + oStreamCursor);
+  P.streamCapacity = (uint32_t) streamCapacity;
   P.bigList = (uint32_t *) (A + oBigList);
   P.bigCount = (uint32_t *) (A + oBigCount);
+  P.bigAll = (uint32_t *) (A + oBigAll);
+  P.bigAllCount = (uint32_t *) (A + oBigAllCount);
   P.bigCapacity = (uint32_t) std::max(primSlots, 1);
+  P.binReserved = (uint32_t *) (A + oBinReserved);
   P.textures = g.dTextures;
   P.counters = g.dCounters;
-  if (g.tileTiming && ct && (size_t) nTiles * 2 <= g.tileTimesCap) P.tileTimes = g.dTileTimes;
+  if (g.tileTiming && ct && (size_t) nTiles * 4 <= g.tileTimesCap) P.tileTimes = g.dTileTimes;
 
   if (depthOnly) {
     if (maxVerts > 0) {
@@ -1200,7 +1215,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     if (maxPrims > 0) {
       SglSetupOut so = {(SglPrim *) (A + oPrims), (SglPrimVerts *) (A + oPrimVerts), (uint32_t *) (A + oPrimKeys)};
       SglSetupShared ss;
-      ss.tileCount = P.tileCount; ss.bigList = P.bigList; ss.bigCount = P.bigCount; ss.bigCapacity = P.bigCapacity;
+      ss.tileCount = P.tileCount; ss.bigList = P.bigAll; ss.bigCount = P.bigAllCount; ss.bigCapacity = P.bigCapacity;
       ss.binReserved = (uint32_t *) (A + oBinReserved); ss.binCapacity = P.binCapacity; ss.overflowHost = g.dOverflow;
       ss.counters = g.dCounters; ss.tilesX = tilesX; ss.tilesY = tilesY; ss.fbW = fbW; ss.fbH = fbH;
       ss.tileOwner = P.tileOwner; ss.rank = g.rank;
@@ -1208,17 +1223,24 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
       if (rc) return rc;
     }
   }
+  const bool anyPrims = nDraws && maxSlots > 0;
+  const int bigGrid = std::min(std::max(primSlots, 1), 148 * 2);
+  if (anyPrims) {   // big primitives: exact per-tile counts before the scan
+    rc = launch("sglBigBinKernel<0>", sglBigBinKernel<0>, dim3(bigGrid), dim3(256), P);
+    if (rc) return rc;
+  }
   rc = launch("sglTileScanKernel", sglTileScanKernel, dim3(1), dim3(1024), (const uint32_t *) P.tileCount, P.tileOffset, nTiles, g.dCounters,
               P.tileOrder, P.tileClassCount, P.tileSortedCount, P.tileOwner, g.rank);
   if (rc) return rc;
-  if (nDraws && maxSlots > 0) {
+  if (anyPrims) {
     rc = launch("sglBinFillKernel", sglBinFillKernel, dim3((maxSlots + 255) / 256, nDraws), dim3(256), P);
     if (rc) return rc;
-  }
-  if (P.splitCap > 0) {   // lists of the tiles the MSAA visibility kernel splits
-    rc = launch("sglTileSortKernel", sglTileSortKernel, dim3((P.splitCap + SGL_TILE_SORT_WARPS - 1) / SGL_TILE_SORT_WARPS), dim3(32 * SGL_TILE_SORT_WARPS), P);
+    rc = launch("sglBigBinKernel<1>", sglBigBinKernel<1>, dim3(bigGrid), dim3(256), P);
     if (rc) return rc;
   }
+  // every tile's list in submission order (one warp per tile)
+  rc = launch("sglTileSortKernel", sglTileSortKernel, dim3((nTiles + SGL_TILE_SORT_WARPS - 1) / SGL_TILE_SORT_WARPS), dim3(32 * SGL_TILE_SORT_WARPS), P);
+  if (rc) return rc;
   rc = toPixelStage();
   if (rc) return rc;
   if (g.auxPending && (!overlap || std::find(g.auxDepthTex.begin(), g.auxDepthTex.end(), g.depthTex) != g.auxDepthTex.end()))

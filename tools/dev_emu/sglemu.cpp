@@ -32,7 +32,7 @@ struct HostAlloc {
   int newVertex(const SglDrawRec &d) { int e = (*d.vertexCounter)++; int i = d.vertexCount + e; return i < d.vertexCap ? i : -1; }
   int newAppendSlots(const SglDrawRec &d, int n) { int a = *d.appendCounter; *d.appendCounter += n; return a + n <= d.appendCap ? d.appendBase + a : -1; }
   void overflow() { overflowCount++; }
-  void binPrim(int, const SglPrim &) {}
+  bool binPrim(int, const SglPrim &) { return false; }
 };
 int levelCount(const SglTextureDesc &d) {
   if (!d.use_mipmaps) return 1;
