@@ -185,6 +185,12 @@ int sgl_pass_end(void);
  * the map is supplied explicitly: owner[ty*tiles_x+tx] == rank.  NULL restores "own everything". */
 int sgl_set_tile_owner_map(const uint8_t *owner, int tiles_x, int tiles_y);
 int sgl_tile_size(void);
+/* Passes into `texture` (as colour or depth attachment) also render the tiles within `pixels` of an owned tile; pixels < 0:
+ * every tile (the texture is replicated on all ranks).  For attachments that LATER passes sample: a screen-space filter
+ * needs the owner's neighbourhood (FXAA reads up to 18.5 px along the edge + its bilinear footprint,
+ * Viewer/Shader/Software/FxaaSoft.h:73-74,169-210: 32 px = two tiles), arbitrary look-ups need the whole image.  Attachments
+ * of a different size than the owner map's frame (shadow maps) are always rendered whole. */
+int sgl_texture_set_shard_halo(int texture, int pixels);
 int sgl_set_rank(int rank, int world);                     /* re-label the context (sgl_init's rank/world) */
 int sgl_tiles_owned(int owner_rank, int *tiles_out);       /* number of tiles `owner_rank` owns in the current map */
 /* Gather of finished tiles to rank 0, NCCL form: tiles of a linear RGBA8 texture (resolved colour for MS targets) owned by

@@ -55,7 +55,7 @@ C_ABI_SYMBOLS = [
     "sgl_buffer_upload", "sgl_buffer_destroy", "sgl_texture_create", "sgl_texture_destroy", "sgl_texture_upload",
     "sgl_texture_gen_mips", "sgl_texture_readback", "sgl_texture_readback_async", "sgl_readback_wait", "sgl_texture_level_size", "sgl_texture_device_ptr",
     "sgl_pass_begin", "sgl_set_viewport", "sgl_draw", "sgl_pass_end", "sgl_set_tile_owner_map", "sgl_tile_size",
-    "sgl_set_rank", "sgl_tiles_owned", "sgl_tiles_pack", "sgl_tiles_unpack", "sgl_texture_set_mirror", "sgl_peer_alloc",
+    "sgl_set_rank", "sgl_texture_set_shard_halo", "sgl_tiles_owned", "sgl_tiles_pack", "sgl_tiles_unpack", "sgl_texture_set_mirror", "sgl_peer_alloc",
     "sgl_peer_free", "sgl_peer_open", "sgl_peer_close", "sgl_peer_signal", "sgl_peer_signal_after_copies", "sgl_peer_wait", "sgl_peer_collect",
     "sgl_peer_timeouts",
     "sgl_kat_barycentric", "sgl_kat_sample", "sgl_kat_blend", "sgl_kat_depth"]

@@ -39,6 +39,8 @@ struct TextureRec {
   SglTexObj obj{};
   size_t bytes = 0;
   void *mirror = nullptr;   // sgl_texture_set_mirror: second destination of the final colour (may be peer memory)
+  int shardHalo = 0;        // sgl_texture_set_shard_halo: pixels around owned tiles that passes into this texture also render
+                            // under a tile-owner map (< 0: every tile -- the texture is replicated)
   cudaEvent_t rbDone = nullptr;   // completion of the last sgl_texture_readback_async on the copy stream
   bool rbPending = false;         // a later pass that overwrites the colour image must wait for rbDone on the device
 };
@@ -107,6 +109,10 @@ struct Ctx {
   uint8_t *dTileOwner = nullptr;
   int ownerTilesX = 0, ownerTilesY = 0;
   std::vector<uint8_t> hostTileOwner;
+  // dilated copies of the owner map for passes into textures with a shard halo: entry == rank for owned tiles and tiles
+  // within the halo, 255 elsewhere (cached per halo width in tiles; dropped when the map or the rank changes)
+  struct HaloMap { int tiles; uint8_t *d; };
+  std::vector<HaloMap> haloMaps;
   uint32_t *dOwnerPrefix = nullptr;   // exclusive count of tiles owned by prefixRank (sgl_tiles_pack / unpack)
   int prefixRank = -1;
   std::vector<void *> peerAllocs, peerMaps;
@@ -216,6 +222,36 @@ int checkOverflow() {
   if (g.clipScale < 64) g.clipScale *= 2;
   return fail(SGL_ERR_OVERFLOW, "a render pass ran out of clip-vertex arena space and dropped primitives "
                                 "(sgl_get_counters().clip_overflow); later passes get a %dx larger arena -- resubmit the frame", g.clipScale);
+}
+
+void dropHaloMaps() {
+  for (auto &h : g.haloMaps) if (h.d) cudaFree(h.d);
+  g.haloMaps.clear();
+}
+
+// owner map for a pass into a texture with `haloPixels` of shard halo (0: the plain map; < 0: null = render every tile)
+int ownerMapForHalo(int haloPixels, const uint8_t **out) {
+  *out = nullptr;
+  if (haloPixels < 0) return SGL_OK;
+  if (haloPixels == 0) { *out = g.dTileOwner; return SGL_OK; }
+  const int ht = (haloPixels + SGL_TILE - 1) / SGL_TILE;
+  for (auto &h : g.haloMaps) if (h.tiles == ht) { *out = h.d; return SGL_OK; }
+  const int tx = g.ownerTilesX, ty = g.ownerTilesY;
+  std::vector<uint8_t> m((size_t) tx * ty, 255);
+  for (int y = 0; y < ty; y++)
+    for (int x = 0; x < tx; x++) {
+      if (g.hostTileOwner[(size_t) y * tx + x] != g.rank) continue;
+      for (int yy = std::max(0, y - ht); yy <= std::min(ty - 1, y + ht); yy++)
+        for (int xx = std::max(0, x - ht); xx <= std::min(tx - 1, x + ht); xx++) m[(size_t) yy * tx + xx] = (uint8_t) g.rank;
+    }
+  Ctx::HaloMap h;
+  h.tiles = ht;
+  h.d = nullptr;
+  CU(cudaMalloc(&h.d, m.size()));
+  CU(cudaMemcpy(h.d, m.data(), m.size(), cudaMemcpyHostToDevice));
+  g.haloMaps.push_back(h);
+  *out = h.d;
+  return SGL_OK;
 }
 
 int ensureArena(Ctx::Arena &a, size_t bytes) {
@@ -439,6 +475,7 @@ int sgl_shutdown(void) {
   if (g.auxDone) cudaEventDestroy(g.auxDone);
   if (g.vis) cudaFree(g.vis);
   if (g.dummyTexels) cudaFree(g.dummyTexels);
+  dropHaloMaps();
   if (g.dTileOwner) cudaFree(g.dTileOwner);
   if (g.dOwnerPrefix) cudaFree(g.dOwnerPrefix);
   if (g.dTileTimes) cudaFree(g.dTileTimes);
@@ -1112,7 +1149,16 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   }
   P.clearDepth = g.clearDepth;
   P.tilesX = tilesX; P.tilesY = tilesY;
-  P.tileOwner = (g.dTileOwner && g.ownerTilesX == tilesX && g.ownerTilesY == tilesY) ? g.dTileOwner : nullptr;
+  P.tileOwner = nullptr;
+  if (g.dTileOwner && g.ownerTilesX == tilesX && g.ownerTilesY == tilesY) {
+    // sort-first sharding: this rank renders its own tiles -- plus, for an attachment that later passes sample around the
+    // pixel they shade (FXAA input), the tiles within the texture's halo; a texture marked "replicated" is rendered whole
+    int halo = 0;
+    if (ct && ct->shardHalo != 0) halo = ct->shardHalo;
+    if (dt && dt->shardHalo != 0 && halo >= 0) halo = dt->shardHalo < 0 ? -1 : std::max(halo, dt->shardHalo);
+    rc = ownerMapForHalo(halo, &P.tileOwner);
+    if (rc) return rc;
+  }
   P.rank = g.rank;
   P.draws = (const SglDrawRec *) (A + oDraws);
   P.drawCount = nDraws;
@@ -1379,6 +1425,7 @@ int sgl_tile_size(void) { return SGL_TILE; }
 int sgl_set_tile_owner_map(const uint8_t *owner, int tiles_x, int tiles_y) {
   NEED_CTX();
   { int rc = syncAll(); if (rc) return rc; }
+  dropHaloMaps();
   if (g.dTileOwner) CU(cudaFree(g.dTileOwner));
   if (g.dOwnerPrefix) CU(cudaFree(g.dOwnerPrefix));
   g.dTileOwner = nullptr;
@@ -1401,8 +1448,21 @@ int sgl_set_tile_owner_map(const uint8_t *owner, int tiles_x, int tiles_y) {
 int sgl_set_rank(int rank, int world) {
   NEED_CTX();
   if (world < 1 || rank < 0 || rank >= world) return fail(SGL_ERR_INVALID, "rank %d of %d", rank, world);
+  if (rank != g.rank) {
+    int rc = syncAll();
+    if (rc) return rc;
+    dropHaloMaps();
+  }
   g.rank = rank;
   g.world = world;
+  return SGL_OK;
+}
+
+int sgl_texture_set_shard_halo(int handle, int pixels) {
+  NEED_CTX();
+  TextureRec *t = tex(handle);
+  if (!t) return fail(SGL_ERR_INVALID, "bad texture handle %d", handle);
+  t->shardHalo = pixels;
   return SGL_OK;
 }
 

@@ -1,4 +1,5 @@
 #include "RendererCUDA.h"
+#include <cstdlib>
 
 #include <cstdio>
 #include <cstring>
@@ -55,6 +56,11 @@ bool TextureCUDA::ensureAllocated() {
     handle_ = 0;
     return false;
   }
+  // An attachment that is also sampled (shadow map, FXAA input, IBL cubes): under sort-first tile sharding a later pass
+  // reads pixels other ranks own, so passes into it render more than the owned tiles -- everything by default, or the
+  // halo the application declared (RendererCUDA::setSampledAttachmentHalo)
+  if ((usage & TextureUsage_Sampler) && (usage & (TextureUsage_AttachmentColor | TextureUsage_AttachmentDepth)))
+    sgl_texture_set_shard_halo(handle_, RendererCUDA::sampledAttachmentHalo());
   return true;
 }
 
@@ -260,7 +266,12 @@ void UniformSamplerCUDA::setTexture(const std::shared_ptr<Texture> &tex) {
 }
 
 // ---- RendererCUDA ----------------------------------------------------------------------------------------------------------
+static int gSampledAttachmentHalo = -1;
+void RendererCUDA::setSampledAttachmentHalo(int pixels) { gSampledAttachmentHalo = pixels; }
+int RendererCUDA::sampledAttachmentHalo() { return gSampledAttachmentHalo; }
+
 bool RendererCUDA::create() {
+  if (const char *h = getenv("SGL_SHARD_HALO")) gSampledAttachmentHalo = atoi(h);   // harness knob (tests, bench)
   if (sgl_init(device_, rank_, world_) != SGL_OK) {
     logError("create");
     return false;

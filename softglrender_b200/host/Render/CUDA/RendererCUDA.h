@@ -152,6 +152,11 @@ class RendererCUDA : public Renderer {
   // device / layout selection for objects created afterwards (SGL_LAYOUT_*; the reference picks at compile time)
   void setDevice(int ordinal, int rank = 0, int world = 1) { device_ = ordinal; rank_ = rank; world_ = world; }
   void setTextureLayout(int layout) { textureLayout_ = layout; }
+  // Multi-GPU tile sharding: how far around the pixel it shades a later pass samples an attachment rendered earlier
+  // (pixels; < 0 = anywhere, the attachment is then rendered whole on every rank -- the default).  A Viewer whose only
+  // screen-space consumer is the FXAA filter declares 32 (FxaaSoft.h:73-74,169-210: 18.5 px + bilinear footprint).
+  static void setSampledAttachmentHalo(int pixels);
+  static int sampledAttachmentHalo();
 
  private:
   int device_ = 0, rank_ = 0, world_ = 1;

@@ -130,6 +130,62 @@ def main():
                     assert np.array_equal(a[r], full), "%s: copy-engine gather, slot %d differs" % (name, r)
             report["%s.dma.frames" % name] = "byte-exact x%d ranks" % world
         p.close()
+
+    # ---- the BASELINE configs tile-sharded over a real process group: config 2 (the shadow map every rank renders whole is
+    #      sampled by the floor) and config 3 (FXAA needs a 32-px halo of its input around the owned tiles)
+    from softglrender_b200 import workloads
+    if workloads.A.find_assets_dir() is not None:
+        shared = os.path.join(ROOT, "build", "tests")
+        cases = (("config2", lambda: workloads.build_c2(os.path.join(shared, "c2")), None),
+                 ("config3", lambda: workloads.build_c3(os.path.join(shared, "c3"), 1920, 1080), 32))
+        for name, build, halo in cases:
+            if rank == 0:
+                build()                      # traces / IBL maps are cached on disk: one rank writes them
+            dist.barrier()
+            trace, data = build()
+            if halo is not None:
+                os.environ["SGL_SHARD_HALO"] = str(halo)
+            p = capi.Player(trace, data)
+            p.setup()
+            tex = p.texture_handle("color")
+            w_, h_ = C.c_int(), C.c_int()
+            capi.check(lib.sgl_texture_level_size(tex, 0, C.byref(w_), C.byref(h_)))
+            w, h = w_.value, h_.value
+            p.frame(sync=True)
+            full = p.readback("color")[0].reshape(h, w, 4).copy()
+            for policy in ("interleave", "bands"):
+                g = M.TileGather(w, h, rank, world, policy)
+                g.install(lib)
+                junk = torch.full((g.max_count * g.tile_bytes,), 0xAB, dtype=torch.uint8, device="cuda")
+                for r in range(world):
+                    capi.check(lib.sgl_tiles_unpack(tex, r, junk.data_ptr(), junk.numel()))
+                p.frame(sync=False)
+                g.gather_device(lib, tex)
+                capi.check(lib.sgl_wait_idle())
+                got = p.readback("color")[0].reshape(h, w, 4)
+                if rank == 0:
+                    assert np.array_equal(got, full), "%s: NCCL tile gather (%s) differs from the 1-GPU frame" % (name, policy)
+                    report["%s.nccl.%s" % (name, policy)] = "byte-exact"
+            g = M.TileGather(w, h, rank, world, "interleave")
+            g.install(lib)
+            store = M.PeerFrameStore(lib, w, h, rank, world, frames_per_slot=1, slots=2, control_group=ctl)
+            frames = []
+            for f in range(4):
+                store.begin_frame(tex, 0)
+                p.frame(sync=False)
+                store.end_frame((lambda ptr: frames.append(M.device_view(ptr, w * h * 4).clone())) if rank == 0 else None)
+            capi.check(lib.sgl_wait_idle())
+            torch.cuda.synchronize()
+            dist.barrier()
+            assert store.timeouts() == 0, "peer wait timed out"
+            if rank == 0:
+                for f, t in enumerate(frames):
+                    assert np.array_equal(t.cpu().numpy().reshape(h, w, 4), full), "%s: direct-store tile gather differs (frame %d)" % (name, f)
+                report["%s.p2p.tiles" % name] = "byte-exact x%d frames" % len(frames)
+            capi.check(lib.sgl_texture_set_mirror(tex, None))
+            capi.check(lib.sgl_set_tile_owner_map(None, 0, 0))
+            os.environ.pop("SGL_SHARD_HALO", None)
+            p.close()
     dist.barrier()
     if rank == 0:
         print("MGPU_OK " + json.dumps(report))

@@ -18,23 +18,23 @@ import make_golden  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name,world,policy", [("kat_ms4_revz", 2, "interleave"), ("kat_ms4_revz", 3, "bands"), ("kat_1x", 4, "interleave")])
-def test_one_gpu_plays_every_rank_in_turn(name, world, policy, work_dir):
-    """Each rank renders only the tiles it owns; packed owned tiles == the same tiles of the unsharded frame, for
-    colour and (through the attachment read-back) per-sample depth."""
+def _play_every_rank(trace, data, world, policy, extra_targets=(), check_depth=True):
+    """One GPU plays every rank of a `world`-way tile-sharded render in turn.  Before each rank's frame the colour target
+    and every intermediate target in `extra_targets` are filled with junk, so anything the frame needs from tiles this
+    rank does not render would show.  Returns (full unsharded frame, frame assembled from the ranks' owned tiles)."""
     import torch
     from softglrender_b200 import capi, multigpu as M
     capi.init(0)
     lib = capi.load()
-    trace, _ = make_golden.build_trace(name, work_dir)
-    p = capi.Player(trace, work_dir)
+    p = capi.Player(trace, data)
     try:
         p.setup()
         tex = p.texture_handle("color")
+        others = [p.texture_handle(t) for t in extra_targets]
         p.frame(sync=True)
         buf, (w, h, _, _) = p.readback("color")
         full = buf.reshape(h, w, 4).copy()
-        depth_full = p.readback("depth")[0].copy()
+        depth_full = p.readback("depth")[0].copy() if check_depth else None
         g = M.TileGather(w, h, 0, world, policy)
         g.install(lib)
         n = g.max_count * g.tile_bytes
@@ -44,30 +44,78 @@ def test_one_gpu_plays_every_rank_in_turn(name, world, policy, work_dir):
         for r in range(world):
             capi.check(lib.sgl_set_rank(r, world))
             for q in range(world):
-                capi.check(lib.sgl_tiles_unpack(tex, q, junk.data_ptr(), n))
+                for t in [tex] + others:
+                    capi.check(lib.sgl_tiles_unpack(t, q, junk.data_ptr(), n))
             p.frame(sync=False)
             cnt = C.c_int()
             capi.check(lib.sgl_tiles_pack(tex, r, stage.data_ptr(), n, C.byref(cnt)))
             capi.check(lib.sgl_wait_idle())
             assert cnt.value == g.counts[r]
             packed = stage.cpu().numpy()[:cnt.value * g.tile_bytes].reshape(cnt.value, M.TILE, M.TILE, 4)
-            want = M.pack_tiles_host(full, g.owner, r)
-            # pixels of edge tiles that lie outside the image are never written by the pack kernel
-            mask = M.pack_tiles_host(np.full_like(full, 1), g.owner, r).astype(bool)
-            assert np.array_equal(packed[mask], want[mask]), "rank %d of %d" % (r, world)
             M.unpack_tiles_host(assembled, packed, g.owner, r)
-            # tiles of other ranks must be untouched (still junk)
-            got = p.readback("color")[0].reshape(h, w, 4)
             other = np.repeat(np.repeat(g.owner != r, M.TILE, axis=0), M.TILE, axis=1)[:h, :w]
-            assert (got[other] == 0xAB).all()
-            # depth of owned pixels is bit-identical to the unsharded frame
-            d = p.readback("depth")[0].reshape(h, w, -1)
-            assert np.array_equal(d[~other], depth_full.reshape(h, w, -1)[~other])
-        assert np.array_equal(assembled, full)
+            # tiles of other ranks must be untouched in the final target (still junk) ...
+            got = p.readback("color")[0].reshape(h, w, 4)
+            assert (got[other] == 0xAB).all(), "rank %d wrote tiles it does not own" % r
+            # ... and the depth of owned pixels is bit-identical to the unsharded frame
+            if check_depth:
+                d = p.readback("depth")[0].reshape(h, w, -1)
+                assert np.array_equal(d[~other], depth_full.reshape(h, w, -1)[~other]), "rank %d of %d" % (r, world)
+        return full, assembled
     finally:
         capi.check(lib.sgl_set_tile_owner_map(None, 0, 0))
         capi.check(lib.sgl_set_rank(0, 1))
         p.close()
+
+
+@pytest.mark.parametrize("name,world,policy", [("kat_ms4_revz", 2, "interleave"), ("kat_ms4_revz", 3, "bands"), ("kat_1x", 4, "interleave")])
+def test_one_gpu_plays_every_rank_in_turn(name, world, policy, work_dir):
+    """Each rank renders only the tiles it owns; the frame assembled from the ranks' packed tiles == the unsharded frame,
+    for colour and (through the attachment read-back) per-sample depth."""
+    trace, _ = make_golden.build_trace(name, work_dir)
+    full, assembled = _play_every_rank(trace, work_dir, world, policy)
+    assert np.array_equal(assembled, full)
+
+
+@pytest.mark.parametrize("world,policy", [(2, "bands"), (4, "interleave")])
+def test_config2_tile_sharded_equals_unsharded(world, policy, work_dir):
+    """Config 2 at full size, tile-sharded: the shadow map the Blinn-Phong floor samples is a different-size attachment and
+    is therefore rendered whole by every rank; the 1920x1080 MSAA frame assembled from the ranks' tiles is byte-identical."""
+    from softglrender_b200 import workloads
+    if workloads.A.find_assets_dir() is None:
+        pytest.skip("assets/ not available")
+    trace, data = workloads.build_c2(os.path.join(work_dir, "c2"))
+    full, assembled = _play_every_rank(trace, data, world, policy)
+    assert full.std() > 5.0
+    assert np.array_equal(assembled, full)
+
+
+@pytest.mark.parametrize("world,policy,halo", [(2, "bands", 32), (4, "interleave", 32), (2, "bands", -1)])
+def test_config3_fxaa_tile_sharded_needs_and_gets_its_halo(world, policy, halo, work_dir, monkeypatch):
+    """Config 3 (3840x2160: shadow pass, opaque + blended main pass into the FXAA input, FXAA pass into the output),
+    tile-sharded: the FXAA pass reads up to 18.5 px + a bilinear footprint around the pixel it shades
+    (FxaaSoft.h:73-74,169-210), so every rank renders a 32-px halo of the FXAA input around its own tiles
+    (sgl_texture_set_shard_halo; halo -1 = the whole input).  The assembled frame is byte-identical to the unsharded one."""
+    from softglrender_b200 import workloads
+    if workloads.A.find_assets_dir() is None:
+        pytest.skip("assets/ not available")
+    monkeypatch.setenv("SGL_SHARD_HALO", str(halo))
+    trace, data = workloads.build_c3(os.path.join(work_dir, "c3"))
+    full, assembled = _play_every_rank(trace, data, world, policy, extra_targets=("color_prefxaa",))
+    assert full.std() > 5.0
+    assert np.array_equal(assembled, full)
+
+
+def test_config3_without_halo_is_wrong_at_tile_borders(work_dir, monkeypatch):
+    """The negative of the test above: with no halo the FXAA pass reads junk across ownership borders (and the test's junk
+    fill makes that visible) -- the halo is what makes sharded config 3 correct, not luck."""
+    from softglrender_b200 import workloads
+    if workloads.A.find_assets_dir() is None:
+        pytest.skip("assets/ not available")
+    monkeypatch.setenv("SGL_SHARD_HALO", "0")
+    trace, data = workloads.build_c3(os.path.join(work_dir, "c3"), 1920, 1080)
+    full, assembled = _play_every_rank(trace, data, 2, "bands", extra_targets=("color_prefxaa",))
+    assert not np.array_equal(assembled, full)
 
 
 def test_unpack_kernel_matches_host_specification():
