@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block (configs 3 and 4 tile-sharded)")
     ap.add_argument("--mgpu", default="frames", choices=["frames", "tiles"],
                     help="N > 1: frame-parallel (weak scaling, default) or one frame sharded by screen tiles (strong scaling)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "dma", "nccl"],
@@ -394,6 +395,24 @@ def main():
     capi.check(lib.sgl_set_profiling(0))
     sync_all()
 
+    # ---- strong scaling of the configs that are DEFINED as one large frame sharded by screen tiles (BASELINE configs 3
+    #      and 4): measured at every N (N = 1: unsharded) so that the driver's per-N lines give the efficiency
+    strong = None
+    if not args.no_strong:
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("bench_configs", os.path.join(ROOT, "tools", "bench_configs.py"))
+            bc = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(bc)
+            capi.check(lib.sgl_texture_set_mirror(color_handle, None))
+            capi.check(lib.sgl_set_tile_owner_map(None, 0, 0))
+            strong = {}
+            for key, n_steps in (("c3", 40), ("c4big", 8)):
+                r = bc.measure_case(lib, key, rank, world, "nccl", steps=n_steps, work=os.path.join(ROOT, "build", "bench"))
+                strong[key] = {k: r[k] for k in ("workload", "n_gpus", "units_per_s", "unit", "steps", "ms_per_step", "gfrag_per_s", "parallelism",
+                                                 "roofline", "kernel_ms_per_step") if k in r}
+        except Exception as e:   # never lose the headline line to the extra block
+            strong = {"error": str(e)[:300]}
     frames_per_step = 1 if tiles or world == 1 else world
     fps = frames_per_step * K / (elapsed_ms / 1000.0)
     frags_per_frame = _sum_over_ranks(ctr["fragments_shaded"], world) / float(K * frames_per_step)
@@ -405,6 +424,8 @@ def main():
             "e2e": {"value": frames_per_step * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d // K,
                     "d2h_bytes_per_step": d2h // K},
             "gpu_launches": launches, "clocks": clocks_summary, "host_submit_ms_per_step": host_submit_ms, "spread": spread, "host_numa": host_numa}
+    if strong is not None:
+        line["strong_scaling"] = strong
     if rank == 0:
         line.update(roofline_blocks(ktimes, ctr, K, elapsed_ms / K, frames_per_step, tiles, world))
         line["kernel_ms_per_frame"] = {k: v[1] / 20.0 for k, v in sorted(ktimes.items())}

@@ -202,60 +202,85 @@ __global__ void __launch_bounds__(256) sglBigBinKernel(SglPassParams P) {
   }
 }
 
-// single CTA: tileOffset = exclusive scan(tileCount); tileOffset[nTiles] = total (clamped entries are dropped later)
-// Also classifies the tiles by bin length (heavy first: SglPassParams::tileOrder) and marks every tile's pre-sorted list
-// as absent; sglTileSortKernel then prepares the lists of the heavy classes only.
+// tileOffset = exclusive scan(tileCount); tileOffset[nTiles] = total.  Single pass over any number of tiles: one CTA per
+// 1024 tiles, chained by decoupled look-back (each CTA publishes its aggregate, then its inclusive prefix, in a 64-bit word
+// {status, value}; a CTA sums the aggregates of its predecessors until it meets a published prefix).  CTAs take their
+// position from a ticket counter, so every predecessor of a waiting CTA is already running.
+// Also classifies the tiles by bin length (heavy first: SglPassParams::tileOrder; each CTA reserves its share of every class
+// list with one atomic) and marks every tile's pre-sorted list as absent until sglTileSortKernel has prepared it.
+// `scanState` (ceil(nTiles / 1024) + 1 words, the last one is the ticket) must be zero on entry.
 __global__ void __launch_bounds__(1024) sglTileScanKernel(const uint32_t *tileCount, uint32_t *tileOffset, int nTiles,
                                                          unsigned long long *counters, uint32_t *tileOrder, uint32_t *tileClassCount,
-                                                         uint32_t *tileSortedCount, const uint8_t *tileOwner, int rank) {
+                                                         uint32_t *tileSortedCount, const uint8_t *tileOwner, int rank,
+                                                         unsigned long long *scanState) {
   __shared__ uint32_t sWarp[32];
-  __shared__ uint32_t sCarry;
-  __shared__ uint32_t sClass[SGL_TILE_CLASSES];   // this CTA is the only writer of the class lists
-  if (threadIdx.x == 0) sCarry = 0;
+  __shared__ uint32_t sPrefix, sPart;
+  __shared__ uint32_t sClass[SGL_TILE_CLASSES], sClassBase[SGL_TILE_CLASSES];
+  const int nParts = (nTiles + 1023) / 1024;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) sPart = (uint32_t) atomicAdd(&scanState[nParts], 1ull);
   if (threadIdx.x < SGL_TILE_CLASSES) sClass[threadIdx.x] = 0;
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < nTiles; base += 1024) {
-    int i = base + threadIdx.x;
-    uint32_t v = i < nTiles ? tileCount[i] : 0u;
-    uint32_t inc = v;
+  const int part = (int) sPart;
+  const int i = part * 1024 + (int) threadIdx.x;
+  const uint32_t v = i < nTiles ? tileCount[i] : 0u;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) sWarp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = sWarp[lane], winc = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
+      uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
     }
-    if (lane == 31) sWarp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = sWarp[lane];
-      uint32_t winc = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
-        if (lane >= o) winc += t;
+    sWarp[lane] = winc - w;   // exclusive
+    if (lane == 31) {
+      // ---- decoupled look-back (one thread: the chain is short, ceil(nTiles / 1024) links)
+      const unsigned long long AGG = 1ull << 62, PRE = 2ull << 62, VAL = (1ull << 62) - 1ull;
+      const uint32_t aggregate = winc;
+      volatile unsigned long long *st = scanState;
+      if (part > 0) {
+        st[part] = AGG | aggregate;
+        __threadfence();
       }
-      sWarp[lane] = winc - w;   // exclusive
-    }
-    __syncthreads();
-    uint32_t carry = sCarry;
-    uint32_t excl = carry + sWarp[warp] + inc - v;
-    if (i < nTiles) {
-      tileOffset[i] = excl;
-      if (tileOrder && !(tileOwner && tileOwner[i] != rank)) {
-        tileSortedCount[i] = SGL_TILE_UNSORTED;
-        const int cls = v >= 184u ? 0 : (v >= 40u ? 1 : (v >= 8u ? 2 : 3));
-        tileOrder[(size_t) cls * nTiles + atomicAdd(&sClass[cls], 1u)] = (uint32_t) i;
+      uint32_t prefix = 0;
+      for (int p = part - 1; p >= 0; p--) {
+        unsigned long long s;
+        while (((s = st[p]) >> 62) == 0ull) { }
+        prefix += (uint32_t) (s & VAL);
+        if ((s >> 62) == 2ull) break;
+      }
+      st[part] = PRE | (unsigned long long) (prefix + aggregate);
+      __threadfence();
+      sPrefix = prefix;
+      if (part == nParts - 1) {
+        tileOffset[nTiles] = prefix + aggregate;
+        atomicAdd(counters + 3, (unsigned long long) (prefix + aggregate));
       }
     }
-    __syncthreads();
-    if (threadIdx.x == 1023) sCarry = excl + v;
-    __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    tileOffset[nTiles] = sCarry;
-    atomicAdd(counters + 3, (unsigned long long) sCarry);
+  __syncthreads();
+  const uint32_t excl = sPrefix + sWarp[warp] + inc - v;
+  int cls = -1;
+  uint32_t pos = 0;
+  if (i < nTiles) {
+    tileOffset[i] = excl;
+    if (tileOrder && !(tileOwner && tileOwner[i] != rank)) {
+      tileSortedCount[i] = SGL_TILE_UNSORTED;
+      cls = v >= 184u ? 0 : (v >= 40u ? 1 : (v >= 8u ? 2 : 3));
+      pos = atomicAdd(&sClass[cls], 1u);
+    }
   }
-  if (tileOrder && threadIdx.x < SGL_TILE_CLASSES) tileClassCount[threadIdx.x] = sClass[threadIdx.x];
+  __syncthreads();
+  if (tileOrder && threadIdx.x < SGL_TILE_CLASSES) sClassBase[threadIdx.x] = sClass[threadIdx.x] ? atomicAdd(&tileClassCount[threadIdx.x], sClass[threadIdx.x]) : 0u;
+  __syncthreads();
+  if (cls >= 0) tileOrder[(size_t) cls * nTiles + sClassBase[cls] + pos] = (uint32_t) i;
 }
 
 // grid = (ceil(maxSlotsPerDraw/256), drawCount): one thread per primitive slot (originals, then appended)

@@ -1026,6 +1026,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   size_t oTileCount = take(sizeof(uint32_t) * nTiles);
   size_t oTileCursor = take(sizeof(uint32_t) * nTiles);
   size_t oTileClassCount = take(sizeof(uint32_t) * SGL_TILE_CLASSES);
+  size_t oScanState = take(sizeof(unsigned long long) * ((nTiles + 1023) / 1024 + 1));   // look-back scan: one word per 1024 tiles + ticket
   size_t zeroBytes = off - oZero;
   size_t oTileOffset = take(sizeof(uint32_t) * (nTiles + 1));
   int primSlots = 0, keyBase = 0, maxVerts = 0, maxPrims = 0, maxSlots = 0;
@@ -1275,8 +1276,8 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     rc = launch("sglBigBinKernel<0>", sglBigBinKernel<0>, dim3(bigGrid), dim3(256), P);
     if (rc) return rc;
   }
-  rc = launch("sglTileScanKernel", sglTileScanKernel, dim3(1), dim3(1024), (const uint32_t *) P.tileCount, P.tileOffset, nTiles, g.dCounters,
-              P.tileOrder, P.tileClassCount, P.tileSortedCount, P.tileOwner, g.rank);
+  rc = launch("sglTileScanKernel", sglTileScanKernel, dim3((nTiles + 1023) / 1024), dim3(1024), (const uint32_t *) P.tileCount, P.tileOffset, nTiles, g.dCounters,
+              P.tileOrder, P.tileClassCount, P.tileSortedCount, P.tileOwner, g.rank, (unsigned long long *) (A + oScanState));
   if (rc) return rc;
   if (anyPrims) {
     rc = launch("sglBinFillKernel", sglBinFillKernel, dim3((maxSlots + 255) / 256, nDraws), dim3(256), P);

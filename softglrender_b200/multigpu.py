@@ -33,7 +33,8 @@ def tile_owner_map(width, height, world, policy="interleave", tile=TILE, block=4
 
     ``interleave``: blocks of ``block`` x ``block`` tiles dealt round-robin along a diagonal-shifted order, so that every
     rank gets an even share of any screen region (the helmet sits in the middle of the frame);
-    ``bands``: contiguous horizontal bands of whole tile rows (what a pass with a screen-space halo, e.g. FXAA, wants).
+    ``bands``: contiguous horizontal bands of whole tile rows; ``stripes[:k]``: k horizontal stripes per rank dealt
+    round-robin (what a pass with a screen-space halo, e.g. FXAA, wants: cheap halo, balanced load).
     """
     tx, ty = tiles_of(width, height, tile)
     if world < 1 or world > 255:
@@ -46,6 +47,16 @@ def tile_owner_map(width, height, world, policy="interleave", tile=TILE, block=4
         owner = np.zeros((ty, tx), np.int64)
         for r in range(world):
             owner[bounds[r]:bounds[r + 1], :] = r
+    elif policy.startswith("stripes"):
+        # k horizontal stripes per rank ("stripes" = 2, "stripes:k"), dealt round-robin, boundaries spread evenly over the
+        # tile rows: contiguous enough that a screen-space halo stays cheap, fine enough that floor, model and sky are
+        # spread over all ranks
+        per_rank = int(policy.split(":")[1]) if ":" in policy else 2
+        n = min(world * per_rank, ty)
+        bounds = [(k * ty) // n for k in range(n + 1)]
+        owner = np.zeros((ty, tx), np.int64)
+        for k in range(n):
+            owner[bounds[k]:bounds[k + 1], :] = k % world
     else:
         raise ValueError("unknown tile ownership policy %r" % policy)
     return np.ascontiguousarray(owner.astype(np.uint8))

@@ -90,7 +90,7 @@ def test_config2_tile_sharded_equals_unsharded(world, policy, work_dir):
     assert np.array_equal(assembled, full)
 
 
-@pytest.mark.parametrize("world,policy,halo", [(2, "bands", 32), (4, "interleave", 32), (2, "bands", -1)])
+@pytest.mark.parametrize("world,policy,halo", [(2, "bands", 32), (4, "interleave", 32), (2, "bands", -1), (3, "stripes", 32)])
 def test_config3_fxaa_tile_sharded_needs_and_gets_its_halo(world, policy, halo, work_dir, monkeypatch):
     """Config 3 (3840x2160: shadow pass, opaque + blended main pass into the FXAA input, FXAA pass into the output),
     tile-sharded: the FXAA pass reads up to 18.5 px + a bilinear footprint around the pixel it shades
