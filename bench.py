@@ -423,7 +423,11 @@ def main():
             "gfrag_per_s": fps * frags_per_frame / 1e9, "fragments_per_frame": frags_per_frame,
             "e2e": {"value": frames_per_step * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d // K,
                     "d2h_bytes_per_step": d2h // K},
-            "gpu_launches": launches, "clocks": clocks_summary, "host_submit_ms_per_step": host_submit_ms, "spread": spread, "host_numa": host_numa}
+            "gpu_launches": launches, "clocks": clocks_summary, "host_submit_ms_per_step": host_submit_ms, "spread": spread, "host_numa": host_numa,
+            # CPU work of the library per step (state snapshots + arena layout + graph launches), without the time the host spends
+            # blocked because the GPU is the bottleneck (the burst figure above includes that)
+            "host_cpu_ms_per_step": (ctr["host_ns_pass_end"] + ctr["host_ns_draw"] - ctr["host_ns_wait_gpu"]) / 1e6 / K,
+            "host_blocked_on_gpu_ms_per_step": ctr["host_ns_wait_gpu"] / 1e6 / K}
     if strong is not None:
         line["strong_scaling"] = strong
     if rank == 0:

@@ -107,6 +107,7 @@ typedef struct SglCounters {
   uint64_t bin_spills;        /* primitives that went to the pass-wide list because the tile bins were full (correct, slower) */
   uint64_t vertices_in;       /* VAO vertices of all submitted draws (64 B each) ... */
   uint64_t indices_in;        /* ... and their indices (4 B each): B_geom of the roofline = 64 * vertices_in + 4 * indices_in */
+  uint64_t host_ns_wait_gpu;  /* part of host_ns_pass_end spent BLOCKED on the GPU (arena ring full): not CPU work */
 } SglCounters;
 
 /* ---- context ---------------------------------------------------------------------------------------- */

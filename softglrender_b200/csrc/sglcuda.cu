@@ -79,6 +79,8 @@ struct Ctx {
     size_t cap = 0;
     cudaEvent_t geomDone = nullptr, pixelDone = nullptr;
     bool used = false;
+    void *stagingHost = nullptr;   // pinned: this slot's draw records (fixed address: the geometry graph's copy node reads it)
+    size_t stagingCap = 0;
   };
   Arena arenas[3];
   int arenaNext = 0;
@@ -96,6 +98,7 @@ struct Ctx {
   cudaEvent_t auxReady = nullptr, auxDone = nullptr;
   bool auxPending = false;
   std::vector<int> auxDepthTex;   // depth textures written by the auxiliary-stream passes not joined yet
+  int noGraphs = 0;            // SGL_NO_GRAPHS=1: every kernel of a stage is launched individually (A/B runs, tests)
   int noOverlap = 0;           // SGL_NO_OVERLAP=1: geometry and pixel stages on one stream (A/B runs)
   int noPassSplit = 0;         // SGL_NO_PASS_SPLIT=1: a pass with a blended tail runs entirely in the fused kernel (A/B runs)
   int noSplit = 0;             // SGL_NO_SPLIT=1: heavy MSAA tiles are not split into quarter-tile CTAs (A/B runs)
@@ -122,7 +125,7 @@ struct Ctx {
   unsigned int *dOverflow = nullptr;   // device alias of hOverflow
   int clipScale = 1;                   // grows after an overflow: clip-vertex / fan arenas of later passes are this much larger
   long long binCapLimit = 0, clipMinVerts = 65536, clipMinFans = 32768;   // sgl_debug_set_limits (tests shrink them)
-  unsigned long long hostLaunches = 0, hostPasses = 0, hostDraws = 0, hostH2D = 0, hostD2H = 0, hostNsPassEnd = 0, hostNsDraw = 0, hostVertices = 0, hostIndices = 0;
+  unsigned long long hostLaunches = 0, hostPasses = 0, hostDraws = 0, hostH2D = 0, hostD2H = 0, hostNsPassEnd = 0, hostNsDraw = 0, hostVertices = 0, hostIndices = 0, hostNsWaitGpu = 0;
   cudaEvent_t evBegin = nullptr, evEnd = nullptr;
   std::string err;
 };
@@ -364,6 +367,92 @@ int launch(const char *name, void (*kernel)(Args...), dim3 grid, dim3 block, Arg
   return SGL_OK;
 }
 
+// ---- stage graphs (submission cost) ---------------------------------------------------------------
+// The kernels of one stage of a pass (memset + record upload + vertex/setup/binning/sort kernels; or the fill + raster
+// kernels of a depth-only pass) are one stream-ordered chain whose launch parameters only depend on the pass "signature"
+// (arena slot, attachment pointers, sizes, draw counts).  The first pass with a given signature captures the chain into a
+// CUDA graph; every later one replays it with ONE cudaGraphLaunch -- the per-draw data (uniform snapshots, pointers) is not
+// part of the graph: it travels in the pinned staging buffer the graph's copy node reads.  Events and cross-stream waits
+// stay outside the graphs, so the scheduling is exactly that of the individually launched kernels.
+// SGL_HOST_PROFILE=1: where sgl_pass_end's CPU time goes (printed at shutdown)
+unsigned long long gHostSec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+const char *gHostSecName[8] = {"layout+records", "staging wait+copy", "geometry stage", "events", "pixel launches", "depth pixel stage", "arena", "-"};
+struct SecTimer {
+  int k;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit SecTimer(int k_) : k(k_) {}
+  void switchTo(int k2) {
+    auto t1 = std::chrono::steady_clock::now();
+    gHostSec[k] += (unsigned long long) std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+    k = k2;
+    t0 = t1;
+  }
+  ~SecTimer() { switchTo(k); }
+};
+
+struct StageGraph {
+  uint64_t key;
+  cudaGraphExec_t exec;
+  unsigned launches;
+  uint64_t lastUse;
+};
+std::vector<StageGraph> gStageGraphs;
+uint64_t gStageClock = 0;
+
+uint64_t hashBytes(uint64_t h, const void *p, size_t n) {   // FNV-1a
+  const unsigned char *b = (const unsigned char *) p;
+  for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+template<typename T> uint64_t hashPod(uint64_t h, const T &v) { return hashBytes(h, &v, sizeof(T)); }
+
+void dropStageGraphs() {
+  for (auto &e : gStageGraphs) cudaGraphExecDestroy(e.exec);
+  gStageGraphs.clear();
+}
+
+// issue() queues the chain on stream `s` through launch() / cudaMemcpyAsync(..., curStream()) only
+template<class F>
+int runStage(cudaStream_t s, uint64_t key, F issue) {
+  struct CurGuard { cudaStream_t saved; ~CurGuard() { gCur = saved; } } guard{gCur};
+  gCur = s;
+  if (g.noGraphs || gProfiling) return issue();
+  for (auto &e : gStageGraphs)
+    if (e.key == key) {
+      e.lastUse = ++gStageClock;
+      g.hostLaunches += e.launches;
+      CU(cudaGraphLaunch(e.exec, s));
+      return SGL_OK;
+    }
+  const unsigned long long before = g.hostLaunches;
+  CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  int rc = issue();
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(s, &graph);
+  if (rc != SGL_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) return fail(SGL_ERR_CUDA, "stage graph capture failed: %s", cudaGetErrorString(e));
+  StageGraph sg;
+  sg.key = key;
+  sg.exec = nullptr;
+  sg.launches = (unsigned) (g.hostLaunches - before);
+  sg.lastUse = ++gStageClock;
+  e = cudaGraphInstantiate(&sg.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(SGL_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  if (gStageGraphs.size() >= 96) {   // bounded cache: drop the least recently used graph
+    size_t lru = 0;
+    for (size_t i = 1; i < gStageGraphs.size(); i++) if (gStageGraphs[i].lastUse < gStageGraphs[lru].lastUse) lru = i;
+    cudaGraphExecDestroy(gStageGraphs[lru].exec);
+    gStageGraphs.erase(gStageGraphs.begin() + lru);
+  }
+  gStageGraphs.push_back(sg);
+  CU(cudaGraphLaunch(sg.exec, s));
+  return SGL_OK;
+}
+
 }  // namespace
 
 namespace {
@@ -432,6 +521,8 @@ int sgl_init(int device_ordinal, int rank, int world) {
   {
     const char *ff = getenv("SGL_FORCE_FUSED");
     g.forceFused = (ff && atoi(ff) != 0) ? 1 : 0;
+    const char *ng = getenv("SGL_NO_GRAPHS");
+    g.noGraphs = (ng && atoi(ng) != 0) ? 1 : 0;
     const char *no = getenv("SGL_NO_OVERLAP");
     g.noOverlap = (no && atoi(no) != 0) ? 1 : 0;
     const char *nps = getenv("SGL_NO_PASS_SPLIT");
@@ -463,7 +554,9 @@ int sgl_shutdown(void) {
   if (g.copyStream) cudaStreamDestroy(g.copyStream);
   if (g.copyReady) cudaEventDestroy(g.copyReady);
   if (g.dTextures) cudaFree(g.dTextures);
+  dropStageGraphs();
   for (auto &a : g.arenas) {
+    if (a.stagingHost) cudaFreeHost(a.stagingHost);
     if (a.mem) cudaFree(a.mem);
     if (a.geomDone) cudaEventDestroy(a.geomDone);
     if (a.pixelDone) cudaEventDestroy(a.pixelDone);
@@ -532,8 +625,14 @@ int sgl_get_counters(SglCounters *out) {
   out->d2h_bytes = g.hostD2H;
   out->host_ns_pass_end = g.hostNsPassEnd;
   out->host_ns_draw = g.hostNsDraw;
+  if (getenv("SGL_HOST_PROFILE") && g.hostPasses) {
+    fprintf(stderr, "[sgl host profile] passes %llu:", g.hostPasses);
+    for (int k = 0; k < 7; k++) fprintf(stderr, " %s %.1f us/pass;", gHostSecName[k], gHostSec[k] / 1e3 / g.hostPasses);
+    fprintf(stderr, "\n");
+  }
   out->bin_spills = c[1];
   out->vertices_in = g.hostVertices;
+  out->host_ns_wait_gpu = g.hostNsWaitGpu;
   out->indices_in = g.hostIndices;
   return checkOverflow();
 }
@@ -542,7 +641,8 @@ int sgl_reset_counters(void) {
   NEED_CTX();
   { int rc = syncAll(); if (rc) return rc; }
   CU(cudaMemset(g.dCounters, 0, 8 * sizeof(unsigned long long)));
-  g.hostLaunches = g.hostPasses = g.hostDraws = g.hostH2D = g.hostD2H = g.hostNsPassEnd = g.hostNsDraw = g.hostVertices = g.hostIndices = 0;
+  for (auto &v : gHostSec) v = 0;
+  g.hostLaunches = g.hostPasses = g.hostDraws = g.hostH2D = g.hostD2H = g.hostNsPassEnd = g.hostNsDraw = g.hostVertices = g.hostIndices = g.hostNsWaitGpu = 0;
   return SGL_OK;
 }
 
@@ -1083,6 +1183,8 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   const size_t streamCapacity = depthOnly ? 0 : std::min<size_t>((size_t) 2 * std::max(primSlots, 1) + (size_t) 16 * nTiles, binCapacity);
   size_t oWork = depthOnly ? 0 : take(sizeof(SglVisWork) * ((size_t) nTiles + 3 * (size_t) splitCap));
   size_t oStream = depthOnly ? 0 : take((size_t) 128 * std::max<size_t>(streamCapacity, 1));
+  SecTimer sec(6);
+  auto section = [&](int k) { sec.switchTo(k); };
   Ctx::Arena &arena = g.arenas[g.arenaNext];
   const cudaStream_t geomStream = g.geomStreams[g.arenaNext];
   g.arenaNext = (g.arenaNext + 1) % 3;
@@ -1097,10 +1199,8 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   gCur = overlap ? geomStream : g.stream;
   if (arena.used && overlap) CU(cudaStreamWaitEvent(geomStream, arena.pixelDone, 0));
   auto toPixelStage = [&]() -> int {   // everything issued so far on the geometry stream precedes what follows
-    if (gCur != g.stream) {
-      CU(cudaEventRecord(arena.geomDone, geomStream));
-      CU(cudaStreamWaitEvent(g.stream, arena.geomDone, 0));
-    }
+    CU(cudaEventRecord(arena.geomDone, gCur ? gCur : g.stream));   // also what the slot's staging buffer waits for on reuse
+    if (gCur != g.stream) CU(cudaStreamWaitEvent(g.stream, arena.geomDone, 0));
     gCur = g.stream;
     return SGL_OK;
   };
@@ -1121,18 +1221,32 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     r.vertexCounter = (int32_t *) (A + oDrawCounters) + 2 * i;
     r.appendCounter = (int32_t *) (A + oDrawCounters) + 2 * i + 1;
   }
-  CU(cudaMemsetAsync(A + oZero, 0, zeroBytes, gCur));
+  section(1);
+  // this slot's pinned staging buffer (fixed address: the geometry graph's copy node reads it).  The previous pass that
+  // used the slot recorded geomDone behind its copy, so one event wait makes the buffer safe to overwrite.
+  const size_t recBytes = sizeof(SglDrawRec) * (size_t) nDraws;
   if (nDraws) {
-    Staging *st = nullptr;
-    rc = stagingAcquire(sizeof(SglDrawRec) * nDraws, &st);
-    if (rc) return rc;
-    memcpy(st->host, draws.data(), sizeof(SglDrawRec) * nDraws);
-    CU(cudaMemcpyAsync(A + oDraws, st->host, sizeof(SglDrawRec) * nDraws, cudaMemcpyHostToDevice, gCur));
-    g.hostH2D += sizeof(SglDrawRec) * nDraws;
-    CU(cudaEventRecord(st->done, gCur));
-    st->pending = true;
+    if (arena.used) {   // normally long complete; when the GPU is the bottleneck this is where the host is throttled
+      HostTimer waitTimer(g.hostNsWaitGpu);
+      CU(cudaEventSynchronize(arena.geomDone));
+    }
+    if (arena.stagingCap < recBytes) {
+      if (arena.stagingHost) CU(cudaFreeHost(arena.stagingHost));
+      arena.stagingHost = nullptr;
+      arena.stagingCap = alignUp(recBytes * 2, 1 << 16);
+      CU(cudaMallocHost(&arena.stagingHost, arena.stagingCap));
+    }
+    memcpy(arena.stagingHost, draws.data(), recBytes);
+    g.hostH2D += recBytes;
   }
+  const cudaStream_t geomS = gCur;
+  auto issueUpload = [&]() -> int {   // head of the geometry chain: zero the counters, upload the draw records
+    CU(cudaMemsetAsync(A + oZero, 0, zeroBytes, curStream()));
+    if (nDraws) CU(cudaMemcpyAsync(A + oDraws, arena.stagingHost, recBytes, cudaMemcpyHostToDevice, curStream()));
+    return SGL_OK;
+  };
 
+  section(0);
   SglPassParams P;
   memset(&P, 0, sizeof(P));
   P.colorBase = ct ? levelPtr(*ct, g.colorLayer, g.colorLevel) : nullptr;
@@ -1192,11 +1306,27 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   P.counters = g.dCounters;
   if (g.tileTiming && ct && (size_t) nTiles * 4 <= g.tileTimesCap) P.tileTimes = g.dTileTimes;
 
+  // signature of the pass for the stage graphs: everything the captured launches depend on
+  uint64_t sig = hashPod(1469598103934665603ull, P);
+  sig = hashPod(sig, A);
+  sig = hashPod(sig, arena.stagingHost);
+  {
+    const long long dims[] = {(long long) oZero, (long long) zeroBytes, (long long) oDraws, (long long) recBytes, nDraws, maxVerts, maxPrims, maxSlots,
+                              nTiles, primSlots, dt ? 1 : 0, depthOnly ? 1 : 0, (long long) oPrims, (long long) oPrimVerts, (long long) oPrimKeys,
+                              (long long) oScanState, (long long) oBinReserved, (long long) oBins, dir};
+    sig = hashBytes(sig, dims, sizeof(dims));
+  }
+
+  section(2);
   if (depthOnly) {
-    if (maxVerts > 0) {
-      rc = launch("sglVertexKernel", sglVertexKernel, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws);
-      if (rc) return rc;
-    }
+    rc = runStage(geomS, hashPod(sig, 0x67656f6dull), [&]() -> int {
+      int r2 = issueUpload();
+      if (r2) return r2;
+      if (maxVerts > 0) return launch("sglVertexKernel", sglVertexKernel, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws);
+      return SGL_OK;
+    });
+    if (rc) return rc;
+    section(3);
     // pixel stage (the atomic rasteriser writes the depth attachment): on the auxiliary stream when overlap is on
     const bool aux = overlap;
     cudaStream_t pix = aux ? g.auxStream : g.stream;
@@ -1208,13 +1338,6 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
       gCur = g.auxStream;
     } else {
       rc = toPixelStage();
-      if (rc) return rc;
-    }
-    if (clearDepthFlag) {
-      uint32_t bits;
-      memcpy(&bits, &g.clearDepth, 4);
-      size_t n = (size_t) fbW * fbH * samples;
-      rc = launch("sglFill32Kernel", sglFill32Kernel, dim3((unsigned) std::min<size_t>((n + 1023) / 1024, 148 * 8)), dim3(256), (uint32_t *) P.depthBase, bits, n);
       if (rc) return rc;
     }
     SglDepthPass D;
@@ -1235,13 +1358,26 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     D.tileOwner = P.tileOwner;
     D.tilesX = tilesX;
     D.rank = g.rank;
-    if (maxPrims > 0) {
-      profBegin(samples == 4 ? "sglDepthOnly<4>" : "sglDepthOnly<1>");
-      int e = sglLaunchDepthOnly(samples, &D, maxPrims, nDraws, nTiles, (void *) pix);
-      profEnd();
-      g.hostLaunches += 3;
-      if (e != 0) return fail(SGL_ERR_CUDA, "depth-only kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
-    }
+    section(5);
+    rc = runStage(pix, hashPod(hashPod(sig, D), 0x70697865ull), [&]() -> int {
+      if (clearDepthFlag) {
+        uint32_t bits;
+        memcpy(&bits, &g.clearDepth, 4);
+        size_t n = (size_t) fbW * fbH * samples;
+        int r2 = launch("sglFill32Kernel", sglFill32Kernel, dim3((unsigned) std::min<size_t>((n + 1023) / 1024, 148 * 8)), dim3(256), (uint32_t *) P.depthBase, bits, n);
+        if (r2) return r2;
+      }
+      if (maxPrims > 0) {
+        profBegin(samples == 4 ? "sglDepthOnly<4>" : "sglDepthOnly<1>");
+        int e = sglLaunchDepthOnly(samples, &D, maxPrims, nDraws, nTiles, (void *) curStream());
+        profEnd();
+        g.hostLaunches += 3;
+        if (e != 0) return fail(SGL_ERR_CUDA, "depth-only kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
+      }
+      return SGL_OK;
+    });
+    if (rc) return rc;
+    section(3);
     if (aux) {
       CU(cudaEventRecord(g.auxDone, g.auxStream));
       CU(cudaEventRecord(arena.pixelDone, g.auxStream));
@@ -1254,40 +1390,45 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     return passDone();
   }
 
-  if (nDraws) {
-    if (maxVerts > 0) {
-      rc = launch("sglVertexKernel", sglVertexKernel, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws);
-      if (rc) return rc;
+  rc = runStage(geomS, hashPod(sig, 0x67656f6dull), [&]() -> int {
+    int r2 = issueUpload();
+    if (r2) return r2;
+    if (nDraws) {
+      if (maxVerts > 0) {
+        r2 = launch("sglVertexKernel", sglVertexKernel, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws);
+        if (r2) return r2;
+      }
+      if (maxPrims > 0) {
+        SglSetupOut so = {(SglPrim *) (A + oPrims), (SglPrimVerts *) (A + oPrimVerts), (uint32_t *) (A + oPrimKeys)};
+        SglSetupShared ss;
+        ss.tileCount = P.tileCount; ss.bigList = P.bigAll; ss.bigCount = P.bigAllCount; ss.bigCapacity = P.bigCapacity;
+        ss.binReserved = (uint32_t *) (A + oBinReserved); ss.binCapacity = P.binCapacity; ss.overflowHost = g.dOverflow;
+        ss.counters = g.dCounters; ss.tilesX = tilesX; ss.tilesY = tilesY; ss.fbW = fbW; ss.fbH = fbH;
+        ss.tileOwner = P.tileOwner; ss.rank = g.rank;
+        r2 = launch("sglSetupKernel", sglSetupKernel, dim3((maxPrims + 127) / 128, nDraws), dim3(128), P.draws, so, ss, dt ? 1 : 0);
+        if (r2) return r2;
+      }
     }
-    if (maxPrims > 0) {
-      SglSetupOut so = {(SglPrim *) (A + oPrims), (SglPrimVerts *) (A + oPrimVerts), (uint32_t *) (A + oPrimKeys)};
-      SglSetupShared ss;
-      ss.tileCount = P.tileCount; ss.bigList = P.bigAll; ss.bigCount = P.bigAllCount; ss.bigCapacity = P.bigCapacity;
-      ss.binReserved = (uint32_t *) (A + oBinReserved); ss.binCapacity = P.binCapacity; ss.overflowHost = g.dOverflow;
-      ss.counters = g.dCounters; ss.tilesX = tilesX; ss.tilesY = tilesY; ss.fbW = fbW; ss.fbH = fbH;
-      ss.tileOwner = P.tileOwner; ss.rank = g.rank;
-      rc = launch("sglSetupKernel", sglSetupKernel, dim3((maxPrims + 127) / 128, nDraws), dim3(128), P.draws, so, ss, dt ? 1 : 0);
-      if (rc) return rc;
+    const bool anyPrims = nDraws && maxSlots > 0;
+    const int bigGrid = std::min(std::max(primSlots, 1), 148 * 2);
+    if (anyPrims) {   // big primitives: exact per-tile counts before the scan
+      r2 = launch("sglBigBinKernel<0>", sglBigBinKernel<0>, dim3(bigGrid), dim3(256), P);
+      if (r2) return r2;
     }
-  }
-  const bool anyPrims = nDraws && maxSlots > 0;
-  const int bigGrid = std::min(std::max(primSlots, 1), 148 * 2);
-  if (anyPrims) {   // big primitives: exact per-tile counts before the scan
-    rc = launch("sglBigBinKernel<0>", sglBigBinKernel<0>, dim3(bigGrid), dim3(256), P);
-    if (rc) return rc;
-  }
-  rc = launch("sglTileScanKernel", sglTileScanKernel, dim3((nTiles + 1023) / 1024), dim3(1024), (const uint32_t *) P.tileCount, P.tileOffset, nTiles, g.dCounters,
-              P.tileOrder, P.tileClassCount, P.tileSortedCount, P.tileOwner, g.rank, (unsigned long long *) (A + oScanState));
+    r2 = launch("sglTileScanKernel", sglTileScanKernel, dim3((nTiles + 1023) / 1024), dim3(1024), (const uint32_t *) P.tileCount, P.tileOffset, nTiles, g.dCounters,
+                P.tileOrder, P.tileClassCount, P.tileSortedCount, P.tileOwner, g.rank, (unsigned long long *) (A + oScanState));
+    if (r2) return r2;
+    if (anyPrims) {
+      r2 = launch("sglBinFillKernel", sglBinFillKernel, dim3((maxSlots + 255) / 256, nDraws), dim3(256), P);
+      if (r2) return r2;
+      r2 = launch("sglBigBinKernel<1>", sglBigBinKernel<1>, dim3(bigGrid), dim3(256), P);
+      if (r2) return r2;
+    }
+    // every tile's list in submission order (one warp per tile)
+    return launch("sglTileSortKernel", sglTileSortKernel, dim3((nTiles + SGL_TILE_SORT_WARPS - 1) / SGL_TILE_SORT_WARPS), dim3(32 * SGL_TILE_SORT_WARPS), P);
+  });
   if (rc) return rc;
-  if (anyPrims) {
-    rc = launch("sglBinFillKernel", sglBinFillKernel, dim3((maxSlots + 255) / 256, nDraws), dim3(256), P);
-    if (rc) return rc;
-    rc = launch("sglBigBinKernel<1>", sglBigBinKernel<1>, dim3(bigGrid), dim3(256), P);
-    if (rc) return rc;
-  }
-  // every tile's list in submission order (one warp per tile)
-  rc = launch("sglTileSortKernel", sglTileSortKernel, dim3((nTiles + SGL_TILE_SORT_WARPS - 1) / SGL_TILE_SORT_WARPS), dim3(32 * SGL_TILE_SORT_WARPS), P);
-  if (rc) return rc;
+  section(3);
   rc = toPixelStage();
   if (rc) return rc;
   if (g.auxPending && (!overlap || std::find(g.auxDepthTex.begin(), g.auxDepthTex.end(), g.depthTex) != g.auxDepthTex.end()))
@@ -1301,6 +1442,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     if (r.rs.blend && ct) deferred = false;
     if (!fill && r.varyingCount != 0) deferred = false;
   }
+  section(4);
   if (deferred) {
     if (ct) {
       size_t need = (size_t) fbW * fbH * samples * sizeof(uint32_t);
