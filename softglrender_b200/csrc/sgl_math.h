@@ -10,7 +10,11 @@
 #if defined(__CUDACC__)
 #define SGL_HD __host__ __device__ __forceinline__
 #define SGL_HDN static __host__ __device__ __noinline__
+#ifdef SGL_SHADE_INLINE
+#define SGL_HDN_T __host__ __device__ __forceinline__
+#else
 #define SGL_HDN_T __host__ __device__ __noinline__
+#endif
 #else
 #define SGL_HD inline
 #define SGL_HDN static

@@ -41,8 +41,24 @@ struct __align__(16) SglVisPrim {   // stream / shared-memory form of a primitiv
   SglPrim p;
   SglTriEdge e;
   uint32_t slot;
-  uint32_t pad;
+  float zBound;     // conservative Hi-Z bound of a depth-tested triangle (sglZBound), NaN = never cull
 };
+
+// Conservative bound of the depth any fragment of triangle p can have, on the side its depth test compares against:
+// LESS / LEQUAL fragments are >= min(z0,z1,z2) - pad, GREATER / GEQUAL fragments <= max + pad.  The interpolated
+// z = (b0 z0 + b1 z1) + b2 z2 has b_i >= 0 and sum b = 1 up to a few ulps (b0 = 1 - (b1 + b2)), so it leaves the vertex range
+// by at most a few 1e-7 * scale; the pad is an order of magnitude above that.  Clamping to [0,1] keeps the bound valid
+// against stored depths (all in [0,1]).  NaN (never cull) for everything else.
+__device__ __forceinline__ float sglZBound(const SglPrim &p) {
+  const uint32_t fl = p.flags;
+  if ((fl & (SGL_PF_KIND_MASK | SGL_PF_DEPTH_TEST)) != (SGL_PK_TRIANGLE | SGL_PF_DEPTH_TEST)) return __int_as_float(0x7fc00000);
+  const uint32_t f = (fl >> SGL_PF_DEPTH_FUNC_SHIFT) & 7u;
+  const float z0 = p.v[0][2], z1 = p.v[1][2], z2 = p.v[2][2];
+  const float pad = 4e-6f * (1.f + fmaxf(fabsf(z0), fmaxf(fabsf(z1), fabsf(z2))));
+  if (f == 1u || f == 3u) return fminf(z0, fminf(z1, z2)) - pad;
+  if (f == 4u || f == 6u) return fmaxf(z0, fmaxf(z1, z2)) + pad;
+  return __int_as_float(0x7fc00000);
+}
 static_assert(sizeof(SglVisPrim) == 128, "stream entries are 128 bytes (cp.async.bulk: 16-byte granules)");
 
 // ---- TMA-style bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier ----------------------------------
@@ -124,7 +140,7 @@ __device__ __forceinline__ void sglStreamStore(SglVisPrim *dst, const SglPrim *p
   if ((v.p.flags & SGL_PF_KIND_MASK) == SGL_PK_TRIANGLE) v.e = sglTriEdge(v.p);
   else memset(&v.e, 0, sizeof(v.e));
   v.slot = slot;
-  v.pad = 0;
+  v.zBound = sglZBound(v.p);
 #pragma unroll
   for (int q = 0; q < 8; q++) reinterpret_cast<uint4 *>(dst)[q] = reinterpret_cast<const uint4 *>(&v)[q];
 }
@@ -444,6 +460,8 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS, SGL_VIS_MIN_BLOCKS) sglVisKe
     P.tileTimes[2 * tile] = t;
   }
 
+  // Hi-Z pays for itself where there is depth complexity: lists of a few primitives (sky, floor, a line) skip its bookkeeping
+  const bool hiz = hasDepth && (!streamed || count >= 32u);
   // cull one staged batch (<= 64 records) against the warp's pixel block, then every pixel (sample) visits the survivors
   auto processBatch = [&](const SglVisPrim *recs, int n) {
     uint32_t rel[2];
@@ -470,14 +488,44 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS, SGL_VIS_MIN_BLOCKS) sglVisKe
       }
       rel[hh] = __ballot_sync(0xffffffffu, r);
     }
+    // Hi-Z over the warp's pixel block: a depth-tested triangle whose conservative depth bound (zBound) cannot pass against
+    // the farthest (LESS / LEQUAL) resp. nearest (GREATER / GEQUAL) depth currently stored in the block fails the test at
+    // every sample of the block -- skipping it changes nothing, in submission order or not.  Stored depths are in [0,1]:
+    // their bit patterns order like the values (-0 mapped to +0); lanes outside the framebuffer are neutral.
+    float wFar, wNear;
+    auto blockDepthRange = [&]() {
+      uint32_t hi = 0u, lo = 0xFFFFFFFFu;
+      if (inFb) {
+        if (NS == 4 && quarterMode) {
+          const uint32_t b = __float_as_uint(depth[0]) == 0x80000000u ? 0u : __float_as_uint(depth[0]);
+          hi = lo = b;
+        } else {
+#pragma unroll
+          for (int s2 = 0; s2 < NS; s2++) {
+            const uint32_t b = __float_as_uint(depth[s2]) == 0x80000000u ? 0u : __float_as_uint(depth[s2]);
+            hi = b > hi ? b : hi;
+            lo = b < lo ? b : lo;
+          }
+        }
+      }
+      wFar = __uint_as_float(__reduce_max_sync(0xffffffffu, hi));
+      wNear = __uint_as_float(__reduce_min_sync(0xffffffffu, lo));
+    };
+    if (hiz) blockDepthRange();
 #pragma unroll
     for (int hh = 0; hh < 2; hh++) {
       uint32_t m = rel[hh];
       while (m) {
         const int k = hh * 32 + __ffs(m) - 1;
         m &= m - 1;
+        if (hiz) {
+          const float zb = recs[k].zBound;                       // NaN: every comparison below is false
+          const uint32_t f = (recs[k].p.flags >> SGL_PF_DEPTH_FUNC_SHIFT) & 7u;
+          if ((f == 1u && zb >= wFar) || (f == 3u && zb > wFar) || (f == 4u && zb <= wNear) || (f == 6u && zb < wNear)) continue;
+        }
         if (NS == 4 && quarterMode) sglVisSamplePrim(P, recs[k], recs[k].slot, px, py, smp, lane, inFb, depth[0], owner[0], hasColor, hasDepth);
         else if (inFb) sglVisPixelPrim<NS>(P, recs[k], recs[k].slot, px, py, depth, owner, hasColor, hasDepth);
+        if (hiz && (recs[k].p.flags & SGL_PF_DEPTH_MASK)) blockDepthRange();
       }
     }
   };
@@ -558,6 +606,7 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS, SGL_VIS_MIN_BLOCKS) sglVisKe
         if (tid < nbb) {
           if ((stage[tid].p.flags & SGL_PF_KIND_MASK) == SGL_PK_TRIANGLE) stage[tid].e = sglTriEdge(stage[tid].p);
           stage[tid].slot = sSlots[b0 + tid];
+          stage[tid].zBound = sglZBound(stage[tid].p);
         }
         __syncthreads();
         processBatch(stage, nbb);

@@ -117,7 +117,7 @@ def measure_case(lib, key, rank, world, gather_mode="nccl", steps=None, cpu=Fals
         frags = int(t.item())
     r = {"workload": name, "n_gpus": world, "units_per_s": units * steps / (elapsed / 1e3), "unit": "views/s" if key == "c5" else "frames/s",
          "steps": steps, "ms_per_step": elapsed / steps, "host_submit_ms_per_step": host_ms, "fragments_per_step": frags / steps,
-         "gfrag_per_s": frags / (elapsed / 1e3) / 1e9, "primitives_per_step": ctr["primitives_in"] / steps,
+         "gfrag_per_s": frags / (elapsed / 1e3) / 1e9, "primitives_per_step": ctr["primitives_in"] / steps, "bin_entries_per_step": ctr["primitives_binned"] / steps,
          "clip_overflow": ctr["clip_overflow"], "bin_spills": ctr["bin_spills"], "host_us_pass_end_per_step": ctr["host_ns_pass_end"] / 1e3 / steps,
          "host_us_draw_per_step": ctr["host_ns_draw"] / 1e3 / steps, "passes_per_step": ctr["passes"] / steps, "draws_per_step": ctr["draws"] / steps,
          "kernel_ms_per_step": {k: v[1] / 3.0 for k, v in sorted(kt.items())}}
