@@ -45,13 +45,6 @@ struct TextureRec {
   bool rbPending = false;         // a later pass that overwrites the colour image must wait for rbDone on the device
 };
 
-struct Staging {
-  void *host = nullptr;
-  size_t cap = 0;
-  cudaEvent_t done = nullptr;
-  bool pending = false;
-};
-
 struct Ctx {
   bool ready = false;
   int refs = 0;              // sgl_init calls not yet matched by sgl_shutdown (several Renderer objects may share the context)
@@ -59,6 +52,9 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   bool ownStream = false;
   cudaStream_t copyStream = nullptr;   // asynchronous read-backs overlap the next frame's geometry / visibility work
+  void *rbStage[2] = {nullptr, nullptr};   // device-side snapshots of an image on its way to the host (see sgl_texture_readback_async)
+  size_t rbStageCap[2] = {0, 0};
+  int rbStageNext = 0;
   cudaEvent_t copyReady = nullptr;
   std::vector<BufferRec> buffers{1};
   std::vector<TextureRec> textures{1};
@@ -106,8 +102,6 @@ struct Ctx {
   uint32_t *vis = nullptr;     // visibility buffer of the deferred path
   size_t visCap = 0;
   int forceFused = 0;          // SGL_FORCE_FUSED=1: always use the fused tile kernel (A/B runs, tests)
-  Staging staging[4];
-  int stagingNext = 0;
   // multi-GPU
   uint8_t *dTileOwner = nullptr;
   int ownerTilesX = 0, ownerTilesY = 0;
@@ -272,23 +266,6 @@ int ensureArena(Ctx::Arena &a, size_t bytes) {
   cudaError_t e = cudaMalloc(&a.mem, ncap);
   if (e != cudaSuccess) return fail(SGL_ERR_OOM, "pass arena of %zu bytes: %s", ncap, cudaGetErrorString(e));
   a.cap = ncap;
-  return SGL_OK;
-}
-
-int stagingAcquire(size_t bytes, Staging **out) {
-  Staging &s = g.staging[g.stagingNext];
-  g.stagingNext = (g.stagingNext + 1) % 4;
-  if (s.pending) {
-    CU(cudaEventSynchronize(s.done));
-    s.pending = false;
-  }
-  if (s.cap < bytes) {
-    if (s.host) CU(cudaFreeHost(s.host));
-    s.cap = alignUp(bytes * 2, 1 << 16);
-    CU(cudaMallocHost(&s.host, s.cap));
-  }
-  if (!s.done) CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-  *out = &s;
   return SGL_OK;
 }
 
@@ -551,6 +528,7 @@ int sgl_shutdown(void) {
     if (t.alive && t.obj.resolve) cudaFree(t.obj.resolve);
     if (t.rbDone) cudaEventDestroy(t.rbDone);
   }
+  for (void *p : g.rbStage) if (p) cudaFree(p);
   if (g.copyStream) cudaStreamDestroy(g.copyStream);
   if (g.copyReady) cudaEventDestroy(g.copyReady);
   if (g.dTextures) cudaFree(g.dTextures);
@@ -576,10 +554,6 @@ int sgl_shutdown(void) {
   for (void *a : g.peerAllocs) cudaFree(a);
   if (g.dCounters) cudaFree(g.dCounters);
   if (g.hOverflow) cudaFreeHost(g.hOverflow);
-  for (auto &s : g.staging) {
-    if (s.host) cudaFreeHost(s.host);
-    if (s.done) cudaEventDestroy(s.done);
-  }
   if (g.evBegin) cudaEventDestroy(g.evBegin);
   if (g.evEnd) cudaEventDestroy(g.evEnd);
   if (g.ownStream && g.stream) cudaStreamDestroy(g.stream);
@@ -966,14 +940,35 @@ int sgl_texture_readback_async(int handle, int layer, int level, int kind, void 
   if (!t->rbDone) CU(cudaEventCreateWithFlags(&t->rbDone, cudaEventDisableTiming));
   CU(cudaEventRecord(g.copyReady, g.stream));
   CU(cudaStreamWaitEvent(g.copyStream, g.copyReady, 0));
-  // cudaMemcpyDefault: the destination may also be device memory -- another GPU's frame store mapped with sgl_peer_open
-  // (copy-engine form of the multi-GPU gather)
-  CU(cudaMemcpyAsync(host_out, src, need, cudaMemcpyDefault, g.copyStream));
-  CU(cudaEventRecord(t->rbDone, g.copyStream));
-  t->rbPending = true;
   cudaPointerAttributes pa;
-  if (cudaPointerGetAttributes(&pa, host_out) != cudaSuccess || pa.type != cudaMemoryTypeDevice) g.hostD2H += need;
+  const bool toDevice = cudaPointerGetAttributes(&pa, host_out) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
   cudaGetLastError();   // unregistered host memory reports an error on old drivers: not ours to keep
+  if (toDevice) {
+    // the destination is device memory -- another GPU's frame store mapped with sgl_peer_open (copy-engine form of the
+    // multi-GPU gather): one copy
+    CU(cudaMemcpyAsync(host_out, src, need, cudaMemcpyDefault, g.copyStream));
+    CU(cudaEventRecord(t->rbDone, g.copyStream));
+  } else {
+    // to the host: the image is first snapshotted into a device staging buffer (microseconds at HBM speed) and the PCIe
+    // copy reads the snapshot.  The next pass that overwrites the image only waits for the snapshot -- with one resolve
+    // buffer and a 170-us PCIe copy of a 1080p frame the shading kernel of frame f+1 otherwise stalls behind the copy of frame f
+    const int k = g.rbStageNext;
+    g.rbStageNext ^= 1;
+    if (g.rbStageCap[k] < need) {
+      CU(cudaStreamSynchronize(g.copyStream));
+      if (g.rbStage[k]) CU(cudaFree(g.rbStage[k]));
+      g.rbStage[k] = nullptr;
+      g.rbStageCap[k] = 0;
+      cudaError_t e = cudaMalloc(&g.rbStage[k], need);
+      if (e != cudaSuccess) return fail(SGL_ERR_OOM, "read-back staging of %zu bytes: %s", need, cudaGetErrorString(e));
+      g.rbStageCap[k] = need;
+    }
+    CU(cudaMemcpyAsync(g.rbStage[k], src, need, cudaMemcpyDeviceToDevice, g.copyStream));
+    CU(cudaEventRecord(t->rbDone, g.copyStream));
+    CU(cudaMemcpyAsync(host_out, g.rbStage[k], need, cudaMemcpyDeviceToHost, g.copyStream));
+    g.hostD2H += need;
+  }
+  t->rbPending = true;
   return SGL_OK;
 }
 
