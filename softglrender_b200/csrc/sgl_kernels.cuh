@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS) sglRasterKernel(SglPassParam
   shaded = __reduce_add_sync(0xffffffffu, shaded);
   if ((tid & 31) == 0 && shaded) atomicAdd(&sShaded, shaded);
   __syncthreads();
-  if (tid == 0 && sShaded) atomicAdd(P.counters + 4, (unsigned long long) sShaded);
+  if (tid == 0 && sShaded) atomicAdd(P.fragCounters + (blockIdx.x & 31), (unsigned long long) sShaded);
 }
 
 #ifndef SGL_RASTER_ONLY

@@ -160,5 +160,6 @@ struct SglPassParams {
   uint32_t streamCapacity;      // entries
   const SglTexObj *textures;
   unsigned long long *counters; // device-side SglCounters mirror
+  unsigned long long *fragCounters;  // [32] fragments shaded, spread over 32 words (one hot word would serialise 65 k warps at one L2 slice)
   unsigned long long *tileTimes; // instrumentation (normally null): [tiles][2] globaltimer ns at CTA start / end of the visibility kernel
 };

@@ -714,5 +714,5 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS, SGL_SHADE_MIN_BLOCKS) sglSha
     }
   }
   shaded = __reduce_add_sync(0xffffffffu, shaded);
-  if (lane == 0 && shaded) atomicAdd(P.counters + 4, (unsigned long long) shaded);
+  if (lane == 0 && shaded) atomicAdd(P.fragCounters + ((blockIdx.x + warp) & 31), (unsigned long long) shaded);
 }

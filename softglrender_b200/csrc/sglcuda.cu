@@ -464,8 +464,8 @@ int sgl_init(int device_ordinal, int rank, int world) {
   g.world = world < 1 ? 1 : world;
   CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   g.ownStream = true;
-  CU(cudaMalloc(&g.dCounters, 8 * sizeof(unsigned long long)));
-  CU(cudaMemset(g.dCounters, 0, 8 * sizeof(unsigned long long)));
+  CU(cudaMalloc(&g.dCounters, 40 * sizeof(unsigned long long)));   // 8 counters + 32 spread fragment counters
+  CU(cudaMemset(g.dCounters, 0, 40 * sizeof(unsigned long long)));
   CU(cudaEventCreate(&g.evBegin));
   CU(cudaEventCreate(&g.evEnd));
   CU(cudaHostAlloc((void **) &g.hOverflow, 64, cudaHostAllocMapped));
@@ -584,9 +584,10 @@ int sgl_wait_idle(void) {
 
 int sgl_get_counters(SglCounters *out) {
   NEED_CTX();
-  unsigned long long c[8];
+  unsigned long long c[40];
   { int rc = syncAll(); if (rc) return rc; }
   CU(cudaMemcpy(c, g.dCounters, sizeof(c), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 32; k++) c[4] += c[8 + k];
   out->passes = g.hostPasses;
   out->draws = g.hostDraws;
   out->primitives_in = c[2];
@@ -614,7 +615,7 @@ int sgl_get_counters(SglCounters *out) {
 int sgl_reset_counters(void) {
   NEED_CTX();
   { int rc = syncAll(); if (rc) return rc; }
-  CU(cudaMemset(g.dCounters, 0, 8 * sizeof(unsigned long long)));
+  CU(cudaMemset(g.dCounters, 0, 40 * sizeof(unsigned long long)));
   for (auto &v : gHostSec) v = 0;
   g.hostLaunches = g.hostPasses = g.hostDraws = g.hostH2D = g.hostD2H = g.hostNsPassEnd = g.hostNsDraw = g.hostVertices = g.hostIndices = g.hostNsWaitGpu = 0;
   return SGL_OK;
@@ -1299,6 +1300,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   P.binReserved = (uint32_t *) (A + oBinReserved);
   P.textures = g.dTextures;
   P.counters = g.dCounters;
+  P.fragCounters = g.dCounters + 8;
   if (g.tileTiming && ct && (size_t) nTiles * 4 <= g.tileTimesCap) P.tileTimes = g.dTileTimes;
 
   // signature of the pass for the stage graphs: everything the captured launches depend on
