@@ -82,14 +82,22 @@ struct SglDeviceAlloc {
     atomicAdd(S.counters + 7, 1ull);
     *(volatile unsigned int *) S.overflowHost = 1u;
   }
-  // Counts the primitive into the bins of the tiles it can touch.  Returns true when it goes to the pass-wide big list
+  // Counts the primitive into the bins of the tiles it can touch.  Returns 1 when it goes to the pass-wide big list
   // instead (SGL_PF_BIG): more than SGL_BIG_PRIM_TILES tiles, or the bin region is exhausted -- the big list holds one
-  // entry per primitive slot at most, so binning can never drop geometry, it only gets slower.
-  __device__ bool binPrim(int slot, const SglPrim &p) {
+  // entry per primitive slot at most, so binning can never drop geometry, it only gets slower.  Returns 2 when the pass is
+  // tile-sharded and none of the tiles the primitive can touch is rendered by this rank: the caller does not emit it.
+  __device__ int binPrim(int slot, const SglPrim &p) {
     int tx0, ty0, tx1, ty1;
-    if (!sglPrimTiles(p, S.fbW, S.fbH, tx0, ty0, tx1, ty1)) return false;
+    if (!sglPrimTiles(p, S.fbW, S.fbH, tx0, ty0, tx1, ty1)) return S.tileOwner ? 2 : 0;
     int n = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
     bool big = n > SGL_BIG_PRIM_TILES;
+    if (!big && S.tileOwner) {     // sharded: look before reserving, most primitives belong to other ranks
+      bool mine = false;
+      for (int ty = ty0; ty <= ty1 && !mine; ty++)
+        for (int tx = tx0; tx <= tx1; tx++)
+          if (S.tileOwner[ty * S.tilesX + tx] == S.rank && sglPrimNearTile(p, tx, ty)) { mine = true; break; }
+      if (!mine) return 2;
+    }
     if (!big) {
       const uint32_t r = sglWarpAggregatedAdd(S.binReserved, (uint32_t) n);
       if (r + (uint32_t) n > S.binCapacity || r + (uint32_t) n < r) { big = true; atomicAdd(S.counters + 1, 1ull); }
@@ -97,7 +105,7 @@ struct SglDeviceAlloc {
     if (big) {   // sglBigBinKernel bins it (or leaves it in the residual list)
       uint32_t b = atomicAdd(S.bigCount, 1u);
       if (b < S.bigCapacity) S.bigList[b] = (uint32_t) slot;
-      return true;
+      return 1;
     }
     for (int ty = ty0; ty <= ty1; ty++)
       for (int tx = tx0; tx <= tx1; tx++) {
@@ -106,17 +114,50 @@ struct SglDeviceAlloc {
         if (!sglPrimNearTile(p, tx, ty)) continue;
         atomicAdd(&S.tileCount[t], 1u);
       }
-    return false;
+    return 0;
   }
 };
 
 // ---------------------------------------------------------------------------------------------------------
 // processVertexShader + perspective divide + viewport transform (RendererSoft.cpp:170-190,259-275,971-992)
-// grid = (ceil(maxVertices/128), drawCount); vertex loads are 4 x LDG.128 (64-byte Vertex, Model.h:20-25)
+// grid = (ceil(maxVertices/128), drawCount); vertex loads are 4 x LDG.128 (64-byte Vertex, Model.h:20-25).
+// POSITION_ONLY: gl_Position, clip mask and screen position from the first 16 bytes of the vertex, no varyings -- depth-only
+// passes (nothing reads varyings) and passes with lazy varyings (SglDrawRec::vertexUsed, sglVaryingKernel).
+template<bool POSITION_ONLY>
 __global__ void __launch_bounds__(128) sglVertexKernel(const SglDrawRec *draws) {
   const SglDrawRec &d = draws[blockIdx.y];
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= d.vertexCount) return;
+  const float4 *src = reinterpret_cast<const float4 *>(d.vertexIn) + (size_t) v * 4;
+  V4 clip;
+  if (POSITION_ONLY) {
+    const float4 q = __ldg(src);
+    const float pos[3] = {q.x, q.y, q.z};
+    clip = sglVertexPosition(d, pos);
+  } else {
+    float attr[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      float4 q = __ldg(src + i);
+      attr[4 * i] = q.x; attr[4 * i + 1] = q.y; attr[4 * i + 2] = q.z; attr[4 * i + 3] = q.w;
+    }
+    float vary[32];
+    clip = sglVertexShader(d, attr, vary);
+    float4 *vo = reinterpret_cast<float4 *>(d.varyings + (size_t) v * d.varyingStride);
+    for (int k = 0; k < d.varyingStride / 4; k++) vo[k] = make_float4(vary[4 * k], vary[4 * k + 1], vary[4 * k + 2], vary[4 * k + 3]);
+  }
+  reinterpret_cast<float4 *>(d.clipPos)[v] = make_float4(clip.x, clip.y, clip.z, clip.w);
+  d.clipMask[v] = sglClipMask(clip);
+  V4 f = sglToScreen(clip, d.vpX, d.vpY, d.vpW, d.vpH);
+  reinterpret_cast<float4 *>(d.fragPos)[v] = make_float4(f.x, f.y, f.z, f.w);
+}
+
+// Lazy varyings: the full vertex shader for the vertices the setup kernel marked (SglDrawRec::vertexUsed) -- in a
+// tile-sharded pass a rank needs the varyings of the primitives that reach its own tiles only.  Same grid as the vertex kernel.
+__global__ void __launch_bounds__(128) sglVaryingKernel(const SglDrawRec *draws) {
+  const SglDrawRec &d = draws[blockIdx.y];
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= d.vertexCount || !d.vertexUsed || !d.vertexUsed[v] || d.varyingStride == 0) return;
   const float4 *src = reinterpret_cast<const float4 *>(d.vertexIn) + (size_t) v * 4;
   float attr[16];
 #pragma unroll
@@ -125,13 +166,9 @@ __global__ void __launch_bounds__(128) sglVertexKernel(const SglDrawRec *draws) 
     attr[4 * i] = q.x; attr[4 * i + 1] = q.y; attr[4 * i + 2] = q.z; attr[4 * i + 3] = q.w;
   }
   float vary[32];
-  V4 clip = sglVertexShader(d, attr, vary);
+  sglVertexShader(d, attr, vary);
   float4 *vo = reinterpret_cast<float4 *>(d.varyings + (size_t) v * d.varyingStride);
   for (int k = 0; k < d.varyingStride / 4; k++) vo[k] = make_float4(vary[4 * k], vary[4 * k + 1], vary[4 * k + 2], vary[4 * k + 3]);
-  reinterpret_cast<float4 *>(d.clipPos)[v] = make_float4(clip.x, clip.y, clip.z, clip.w);
-  d.clipMask[v] = sglClipMask(clip);
-  V4 f = sglToScreen(clip, d.vpX, d.vpY, d.vpW, d.vpH);
-  reinterpret_cast<float4 *>(d.fragPos)[v] = make_float4(f.x, f.y, f.z, f.w);
 }
 
 // grid = (ceil(maxInputPrims/128), drawCount)
@@ -150,9 +187,10 @@ __global__ void __launch_bounds__(128) sglSetupKernel(const SglDrawRec *draws, S
 // of entries; if the bins cannot take them the primitive moves to the residual list (bigList) that every tile kernel
 // scans, else the per-tile counts are raised.  FILL = 1 (after the scan): writes the slots.  Residual primitives are
 // marked in bigAll by their top bit.
+#define SGL_BIGBIN_THREADS 1024
 template<int FILL>
-__global__ void __launch_bounds__(256) sglBigBinKernel(SglPassParams P) {
-  __shared__ uint32_t sWarp[8];
+__global__ void __launch_bounds__(SGL_BIGBIN_THREADS) sglBigBinKernel(SglPassParams P) {
+  __shared__ uint32_t sWarp[SGL_BIGBIN_THREADS / 32];
   __shared__ uint32_t sOk;
   uint32_t nBig = *P.bigAllCount;
   if (nBig > P.bigCapacity) nBig = P.bigCapacity;
@@ -167,7 +205,7 @@ __global__ void __launch_bounds__(256) sglBigBinKernel(SglPassParams P) {
     const int w = tx1 - tx0 + 1, n = w * (ty1 - ty0 + 1);
     if (!FILL) {
       uint32_t cnt = 0;
-      for (int k = tid; k < n; k += 256) {
+      for (int k = tid; k < n; k += SGL_BIGBIN_THREADS) {
         const int tx = tx0 + k % w, ty = ty0 + k / w, t = ty * P.tilesX + tx;
         if (P.tileOwner && P.tileOwner[t] != P.rank) continue;
         if (sglPrimNearTile(p, tx, ty)) cnt++;
@@ -178,7 +216,7 @@ __global__ void __launch_bounds__(256) sglBigBinKernel(SglPassParams P) {
       __syncthreads();
       if (tid == 0) {
         uint32_t total = 0;
-        for (int k = 0; k < 8; k++) total += sWarp[k];
+        for (int k = 0; k < SGL_BIGBIN_THREADS / 32; k++) total += sWarp[k];
         const uint32_t r = atomicAdd(P.binReserved, total);
         const bool ok = r + total <= P.binCapacity && r + total >= r;
         if (!ok) {
@@ -192,7 +230,7 @@ __global__ void __launch_bounds__(256) sglBigBinKernel(SglPassParams P) {
       __syncthreads();
       if (!sOk) continue;
     }
-    for (int k = tid; k < n; k += 256) {
+    for (int k = tid; k < n; k += SGL_BIGBIN_THREADS) {
       const int tx = tx0 + k % w, ty = ty0 + k / w, t = ty * P.tilesX + tx;
       if (P.tileOwner && P.tileOwner[t] != P.rank) continue;
       if (!sglPrimNearTile(p, tx, ty)) continue;

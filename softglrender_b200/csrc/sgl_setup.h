@@ -224,12 +224,19 @@ template<class Alloc>
 SGL_HD void sglEmitPrim(const SglSetupOut &o, Alloc &alloc, const SglDrawRec &d, int slot, uint32_t key, const SglPrim &p,
                         int i0, int i1, int i2) {
   if (!Alloc::kRecords) { alloc.consume(d, p); return; }   // immediate-mode consumers (depth-only atomic path)
+  const int binned = alloc.binPrim(slot, p);     // 0: counted into its tiles, 1: big list, 2: touches no tile this rank renders
+  if (binned == 2) return;                       // the slot stays invalid (flags = 0), nobody will ask for its varyings
   SglPrimVerts pv = {(uint32_t) i0, (uint32_t) i1, (uint32_t) i2, 0u};
   o.primVerts[slot] = pv;
   o.primKeys[slot] = key;
   SglPrim q = p;
-  if (alloc.binPrim(slot, p)) q.flags |= SGL_PF_BIG;
+  if (binned == 1) q.flags |= SGL_PF_BIG;
   o.prims[slot] = q;
+  if (d.vertexUsed) {                            // clip-generated vertices (index >= vertexCount) already have their varyings
+    if (i0 < d.vertexCount) d.vertexUsed[i0] = 1;
+    if (i1 < d.vertexCount) d.vertexUsed[i1] = 1;
+    if (i2 < d.vertexCount) d.vertexUsed[i2] = 1;
+  }
 }
 
 // Everything RendererSoft::draw() does for input primitive `i` of draw `drawIdx` between the vertex stage and

@@ -60,6 +60,21 @@ SGL_HD V3 sglMat3MulCols(const float *c0, const float *c1, const float *c2, V3 v
             fmaf(v.z, c2[2], fmaf(v.x, c0[2], v.y * c1[2])));
 }
 
+// gl_Position alone (same arithmetic as sglVertexShader): what the geometry stage needs before it knows which vertices
+// belong to primitives that survive clipping / culling / tile ownership.  Reads vin[0..2] only.
+SGL_HD V4 sglVertexPosition(const SglDrawRec &d, const float *vin) {
+  float px = vin[0], py = vin[1], pz = vin[2];
+  if (d.shader == SGL_SHADER_FXAA) return v4(px, py, pz, 1.0f);
+  V4 pos = xMat4MulPoint(uMat(d, 80), px, py, pz);
+  if (d.shader == SGL_SHADER_SKYBOX) {
+    V4 r = v4(pos.x, pos.y, pos.w, pos.w);
+    if (uI(d, 0)) r.z = 0.f;
+    return r;
+  }
+  if (d.shader == SGL_SHADER_IBL_IRRADIANCE || d.shader == SGL_SHADER_IBL_PREFILTER) return v4(pos.x, pos.y, pos.w, pos.w);
+  return pos;
+}
+
 SGL_HD V4 sglVertexShader(const SglDrawRec &d, const float *vin, float *vout) {
   const float *mvp = uMat(d, 80);
   float px = vin[0], py = vin[1], pz = vin[2];

@@ -95,7 +95,9 @@ struct __attribute__((aligned(16))) SglDrawRec {
   float pointSize;
   uint32_t fastSamplers;                  // bit s: sampler slot s is "simple" (sgl_texture.h split-phase taps); prefilter
                                           // slot: LINEAR or LINEAR_MIPMAP_LINEAR
-  int32_t pad[2];
+  uint8_t *vertexUsed;                    // lazy varyings (tile-sharded passes): one byte per VAO vertex, set by the setup kernel for
+                                          // the vertices of emitted primitives; sglVaryingKernel then runs the full vertex shader for
+                                          // those only.  null: the vertex kernel writes every vertex's varyings itself
 };
 
 // One unit of work of the visibility kernel, written in heavy-first order by sglTileSortKernel (geometry stage)

@@ -97,6 +97,7 @@ struct Ctx {
   int noGraphs = 0;            // SGL_NO_GRAPHS=1: every kernel of a stage is launched individually (A/B runs, tests)
   int noOverlap = 0;           // SGL_NO_OVERLAP=1: geometry and pixel stages on one stream (A/B runs)
   int noPassSplit = 0;         // SGL_NO_PASS_SPLIT=1: a pass with a blended tail runs entirely in the fused kernel (A/B runs)
+  int noLazyVaryings = 0;      // SGL_NO_LAZY_VARYINGS=1: tile-sharded passes shade every vertex up front (A/B runs)
   int noSplit = 0;             // SGL_NO_SPLIT=1: heavy MSAA tiles are not split into quarter-tile CTAs (A/B runs)
   void *dummyTexels = nullptr; // backing store of texture table entry 0
   uint32_t *vis = nullptr;     // visibility buffer of the deferred path
@@ -506,6 +507,8 @@ int sgl_init(int device_ordinal, int rank, int world) {
     g.noPassSplit = (nps && atoi(nps) != 0) ? 1 : 0;
     const char *ns = getenv("SGL_NO_SPLIT");
     g.noSplit = (ns && atoi(ns) != 0) ? 1 : 0;
+    const char *nl = getenv("SGL_NO_LAZY_VARYINGS");
+    g.noLazyVaryings = (nl && atoi(nl) != 0) ? 1 : 0;
   }
   g.ready = true;
   g.refs = 1;
@@ -1108,6 +1111,19 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
       depthOnly = false;
     dir = d;
   }
+  // sort-first sharding: this rank renders its own tiles -- plus, for an attachment that later passes sample around the
+  // pixel they shade (FXAA input), the tiles within the texture's halo; a texture marked "replicated" is rendered whole
+  const uint8_t *tileOwner = nullptr;
+  if (g.dTileOwner && g.ownerTilesX == tilesX && g.ownerTilesY == tilesY) {
+    int halo = 0;
+    if (ct && ct->shardHalo != 0) halo = ct->shardHalo;
+    if (dt && dt->shardHalo != 0 && halo >= 0) halo = dt->shardHalo < 0 ? -1 : std::max(halo, dt->shardHalo);
+    int rc0 = ownerMapForHalo(halo, &tileOwner);
+    if (rc0) return rc0;
+  }
+  // lazy varyings: in a sharded pass most primitives reach none of this rank's tiles, so the vertex kernel computes
+  // positions only and sglVaryingKernel runs the full vertex shader for the vertices of the primitives that were emitted
+  const bool lazyVaryings = tileOwner != nullptr && !depthOnly && !g.noLazyVaryings;
   // ---- arena layout
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = alignUp(off + bytes, 256); return o; };
@@ -1126,7 +1142,8 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   size_t zeroBytes = off - oZero;
   size_t oTileOffset = take(sizeof(uint32_t) * (nTiles + 1));
   int primSlots = 0, keyBase = 0, maxVerts = 0, maxPrims = 0, maxSlots = 0;
-  std::vector<size_t> oClip(nDraws), oFrag(nDraws), oMask(nDraws), oVout(nDraws), oVary(nDraws);
+  std::vector<size_t> oClip(nDraws), oFrag(nDraws), oMask(nDraws), oVout(nDraws), oVary(nDraws), oUsed(nDraws);
+  size_t usedBytes = 0;
   for (int i = 0; i < nDraws; i++) {
     SglDrawRec &r = draws[i];
     const int pt = r.rs.primitive_type;
@@ -1153,6 +1170,8 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     oMask[i] = take((size_t) r.vertexCap * 4);
     oVout[i] = take((size_t) std::max(extraVerts, 1) * 64);
     oVary[i] = take((size_t) r.vertexCap * std::max(r.varyingStride, 1) * 4);
+    oUsed[i] = usedBytes;
+    if (lazyVaryings) usedBytes = alignUp(usedBytes + (size_t) r.vertexCount, 16);
     g.hostVertices += (unsigned long long) r.vertexCount;
     g.hostIndices += (unsigned long long) r.indexCount;
     maxVerts = std::max(maxVerts, r.vertexCount);
@@ -1160,6 +1179,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     maxSlots = std::max(maxSlots, r.inputPrims * r.slotsPerPrim + r.appendCap);
   }
   if (primSlots >= (1 << 29)) return fail(SGL_ERR_OVERFLOW, "too many primitive slots in one pass (%d)", primSlots);
+  size_t oUsedAll = take(std::max<size_t>(usedBytes, 1));
   size_t oPrims = take(sizeof(SglPrim) * std::max(primSlots, 1));
   size_t oPrimVerts = take(sizeof(SglPrimVerts) * std::max(primSlots, 1));
   size_t oPrimKeys = take(sizeof(uint32_t) * std::max(primSlots, 1));
@@ -1214,6 +1234,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     r.clipMask = (int32_t *) (A + oMask[i]);
     r.vertexOut = (float *) (A + oVout[i]);
     r.varyings = (float *) (A + oVary[i]);
+    r.vertexUsed = lazyVaryings ? A + oUsedAll + oUsed[i] : nullptr;
     r.vertexCounter = (int32_t *) (A + oDrawCounters) + 2 * i;
     r.appendCounter = (int32_t *) (A + oDrawCounters) + 2 * i + 1;
   }
@@ -1238,6 +1259,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   const cudaStream_t geomS = gCur;
   auto issueUpload = [&]() -> int {   // head of the geometry chain: zero the counters, upload the draw records
     CU(cudaMemsetAsync(A + oZero, 0, zeroBytes, curStream()));
+    if (lazyVaryings && usedBytes) CU(cudaMemsetAsync(A + oUsedAll, 0, usedBytes, curStream()));
     if (nDraws) CU(cudaMemcpyAsync(A + oDraws, arena.stagingHost, recBytes, cudaMemcpyHostToDevice, curStream()));
     return SGL_OK;
   };
@@ -1260,16 +1282,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   }
   P.clearDepth = g.clearDepth;
   P.tilesX = tilesX; P.tilesY = tilesY;
-  P.tileOwner = nullptr;
-  if (g.dTileOwner && g.ownerTilesX == tilesX && g.ownerTilesY == tilesY) {
-    // sort-first sharding: this rank renders its own tiles -- plus, for an attachment that later passes sample around the
-    // pixel they shade (FXAA input), the tiles within the texture's halo; a texture marked "replicated" is rendered whole
-    int halo = 0;
-    if (ct && ct->shardHalo != 0) halo = ct->shardHalo;
-    if (dt && dt->shardHalo != 0 && halo >= 0) halo = dt->shardHalo < 0 ? -1 : std::max(halo, dt->shardHalo);
-    rc = ownerMapForHalo(halo, &P.tileOwner);
-    if (rc) return rc;
-  }
+  P.tileOwner = tileOwner;
   P.rank = g.rank;
   P.draws = (const SglDrawRec *) (A + oDraws);
   P.drawCount = nDraws;
@@ -1310,7 +1323,8 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   {
     const long long dims[] = {(long long) oZero, (long long) zeroBytes, (long long) oDraws, (long long) recBytes, nDraws, maxVerts, maxPrims, maxSlots,
                               nTiles, primSlots, dt ? 1 : 0, depthOnly ? 1 : 0, (long long) oPrims, (long long) oPrimVerts, (long long) oPrimKeys,
-                              (long long) oScanState, (long long) oBinReserved, (long long) oBins, dir};
+                              (long long) oScanState, (long long) oBinReserved, (long long) oBins, dir, (long long) oUsedAll, (long long) usedBytes,
+                              lazyVaryings ? 1 : 0};
     sig = hashBytes(sig, dims, sizeof(dims));
   }
 
@@ -1319,7 +1333,8 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     rc = runStage(geomS, hashPod(sig, 0x67656f6dull), [&]() -> int {
       int r2 = issueUpload();
       if (r2) return r2;
-      if (maxVerts > 0) return launch("sglVertexKernel", sglVertexKernel, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws);
+      if (maxVerts > 0)      // nothing in a depth-only pass reads varyings
+        return launch("sglVertexKernel<1>", sglVertexKernel<true>, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws);
       return SGL_OK;
     });
     if (rc) return rc;
@@ -1392,7 +1407,8 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     if (r2) return r2;
     if (nDraws) {
       if (maxVerts > 0) {
-        r2 = launch("sglVertexKernel", sglVertexKernel, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws);
+        r2 = lazyVaryings ? launch("sglVertexKernel<1>", sglVertexKernel<true>, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws)
+                          : launch("sglVertexKernel<0>", sglVertexKernel<false>, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws);
         if (r2) return r2;
       }
       if (maxPrims > 0) {
@@ -1404,12 +1420,16 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
         ss.tileOwner = P.tileOwner; ss.rank = g.rank;
         r2 = launch("sglSetupKernel", sglSetupKernel, dim3((maxPrims + 127) / 128, nDraws), dim3(128), P.draws, so, ss, dt ? 1 : 0);
         if (r2) return r2;
+        if (lazyVaryings && maxVerts > 0) {
+          r2 = launch("sglVaryingKernel", sglVaryingKernel, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws);
+          if (r2) return r2;
+        }
       }
     }
     const bool anyPrims = nDraws && maxSlots > 0;
     const int bigGrid = std::min(std::max(primSlots, 1), 148 * 2);
     if (anyPrims) {   // big primitives: exact per-tile counts before the scan
-      r2 = launch("sglBigBinKernel<0>", sglBigBinKernel<0>, dim3(bigGrid), dim3(256), P);
+      r2 = launch("sglBigBinKernel<0>", sglBigBinKernel<0>, dim3(bigGrid), dim3(SGL_BIGBIN_THREADS), P);
       if (r2) return r2;
     }
     r2 = launch("sglTileScanKernel", sglTileScanKernel, dim3((nTiles + 1023) / 1024), dim3(1024), (const uint32_t *) P.tileCount, P.tileOffset, nTiles, g.dCounters,
@@ -1418,7 +1438,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     if (anyPrims) {
       r2 = launch("sglBinFillKernel", sglBinFillKernel, dim3((maxSlots + 255) / 256, nDraws), dim3(256), P);
       if (r2) return r2;
-      r2 = launch("sglBigBinKernel<1>", sglBigBinKernel<1>, dim3(bigGrid), dim3(256), P);
+      r2 = launch("sglBigBinKernel<1>", sglBigBinKernel<1>, dim3(bigGrid), dim3(SGL_BIGBIN_THREADS), P);
       if (r2) return r2;
     }
     // every tile's list in submission order (one warp per tile)

@@ -299,6 +299,23 @@ class PeerFrameStore:
         if self.rank == 0:
             self._collect(self.frame_no - 1, consume)
 
+    def close(self):
+        """Unmap / free the store and the flags.  Every rank must be idle (sgl_wait_idle + a barrier) before ANY rank calls
+        this: the mappings of the other ranks die with the owner's allocation."""
+        lib = self.lib
+        if self.rank != 0:
+            if self.store:
+                lib.sgl_peer_close(self.store)
+        else:
+            for r, p in enumerate(self.peer_flags):
+                if r != 0:
+                    lib.sgl_peer_close(C.c_void_p(p))
+            if self.store:
+                lib.sgl_peer_free(self.store)
+        if self.local_flag:
+            lib.sgl_peer_free(self.local_flag)
+        self.store, self.local_flag, self.peer_flags, self._peer_array = C.c_void_p(), C.c_void_p(), [], None
+
     def timeouts(self):
         from . import capi
         n = C.c_uint64()

@@ -33,7 +33,7 @@ def case_table(work, rank, world):
     }
 
 
-def measure_case(lib, key, rank, world, gather_mode="nccl", steps=None, cpu=False, keep_trace=False, work=None):
+def measure_case(lib, key, rank, world, gather_mode="nccl", steps=None, cpu=False, keep_trace=False, work=None, control_group=None):
     """One secondary workload on `world` GPUs (torch.distributed already initialised by the caller when world > 1; the
     library must run on torch's current stream).  c3 / c4*: ONE frame sharded by screen tiles, owned tiles gathered to rank 0
     inside the timed region (strong scaling); c5: views dealt to the ranks.  Returns the result dict (same on every rank)."""
@@ -58,19 +58,33 @@ def measure_case(lib, key, rank, world, gather_mode="nccl", steps=None, cpu=Fals
     p = capi.Player(trace, data)
     p.setup()
     tex = p.texture_handle("color") if key != "c5" else p.texture_handle("color_v0")
-    gather = None
+    gather = store = None
     if world > 1 and shard:
         w_, h_ = C.c_int(), C.c_int()
         capi.check(lib.sgl_texture_level_size(tex, 0, C.byref(w_), C.byref(h_)))
         gather = M.TileGather(w_.value, h_.value, rank, world, shard)
         gather.install(lib)
+        if gather_mode == "p2p":
+            # owned pixels are stored straight into rank 0's HBM by the kernel that produces them (multigpu.PeerFrameStore);
+            # rank 0 collects frame f - 1 while frame f renders
+            try:
+                store = M.PeerFrameStore(lib, w_.value, h_.value, rank, world, frames_per_slot=1, slots=3, control_group=control_group,
+                                         lag=1, timeout_ms=20000)
+            except RuntimeError:      # CUDA IPC not permitted here (all ranks agree): NCCL moves the same bytes
+                gather_mode = "nccl"
 
     def step():
+        if store is not None:
+            store.begin_frame(tex, 0)
         p.frame(sync=False)
-        if gather is not None and gather_mode == "nccl":
+        if store is not None:
+            store.end_frame()
+        elif gather is not None and gather_mode == "nccl":
             gather.gather_device(lib, tex)
 
     def sync():
+        if store is not None:
+            store.flush()
         capi.check(lib.sgl_wait_idle())
         if world > 1:
             torch.cuda.synchronize()
@@ -90,6 +104,8 @@ def measure_case(lib, key, rank, world, gather_mode="nccl", steps=None, cpu=Fals
     capi.check(lib.sgl_timer_begin())
     for _ in range(steps):
         step()
+    if store is not None:
+        store.flush()
     capi.check(lib.sgl_timer_end(ms))
     sync()
     elapsed = ms.value
@@ -100,11 +116,22 @@ def measure_case(lib, key, rank, world, gather_mode="nccl", steps=None, cpu=Fals
     ctr = capi.counters()
     capi.check(lib.sgl_set_profiling(1))
     for _ in range(3):
-        p.frame(sync=False)
+        step()
+    if store is not None:
+        store.flush()
     capi.check(lib.sgl_wait_idle())
     kt = capi.kernel_times()
     capi.check(lib.sgl_set_profiling(0))
     sync()
+    if store is not None:
+        if store.timeouts():
+            raise RuntimeError("bench_configs: %d peer waits timed out on rank %d" % (store.timeouts(), rank))
+        capi.check(lib.sgl_texture_set_mirror(tex, None))
+        if rank != 0:                   # mappings go before the owner's allocation
+            store.close()
+        dist.barrier()
+        if rank == 0:
+            store.close()
     if gather is not None:
         capi.check(lib.sgl_set_tile_owner_map(None, 0, 0))
     p.close()
@@ -124,7 +151,8 @@ def measure_case(lib, key, rank, world, gather_mode="nccl", steps=None, cpu=Fals
     if world > 1:
         r["parallelism"] = ("view-parallel, no exchange (every view stays in the HBM of the rank that rendered it)" if key == "c5" else
                             "one frame sharded by screen tiles (%s), geometry replicated, owned tiles gathered to rank 0 by %s inside the timed region"
-                            % (shard, "pack -> NCCL gather -> unpack" if gather_mode == "nccl" else "nothing (gather off)"))
+                            % (shard, {"nccl": "pack -> NCCL gather -> unpack", "p2p": "direct peer stores from the shading kernel into rank 0's HBM (CUDA IPC over NVLink)"}
+                                        .get(gather_mode, "nothing (gather off)")))
     if key.startswith("c4"):
         # B_geom = 64 B x vertices + 4 B x indices, B_out = 4 B x W x H; B_tex left out (lower bound)
         b = 64.0 * ctr["vertices_in"] / steps + 4.0 * ctr["indices_in"] / steps + 4.0 * (7680 * 4320 if key != "c4" else 1920 * 1080)
@@ -151,7 +179,7 @@ def main():
     ap.add_argument("--cpu", action="store_true", help="also time oracle/_ref/ref_player (all host cores)")
     ap.add_argument("--only", default="c1,c3,c4,c4big,c5")
     ap.add_argument("--out", default="")
-    ap.add_argument("--gather", default="nccl", choices=["nccl", "none"], help="N > 1, tile-sharded configs: how owned tiles reach rank 0")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p", "none"], help="N > 1, tile-sharded configs: how owned tiles reach rank 0")
     args = ap.parse_args()
     rank, local, world = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     from softglrender_b200 import capi
@@ -161,6 +189,7 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctl = dist.new_group(backend="gloo") if world > 1 else None      # control plane (IPC handles)
     capi.init(local, rank, world)
     lib = capi.load()
     if world > 1:
@@ -169,7 +198,7 @@ def main():
         capi.check(lib.sgl_set_stream(C.c_void_p(stream.cuda_stream)))
     results = {}
     for key in args.only.split(","):
-        r = measure_case(lib, key, rank, world, args.gather, cpu=args.cpu)
+        r = measure_case(lib, key, rank, world, args.gather, cpu=args.cpu, control_group=ctl)
         results[key] = r
         if rank == 0:
             print(key, json.dumps(r), flush=True)

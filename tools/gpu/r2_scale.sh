@@ -20,4 +20,4 @@ try:
 except Exception as e:
     print("configs failed", e)
 PY
-tail -2 gpurun_out/r02_bench_n${N}_frames.err gpurun_out/r02_configs_n${N}.log
+for f in gpurun_out/r02_bench_n${N}_frames.err gpurun_out/r02_configs_n${N}.log; do tail -n 2 "$f"; done; true
