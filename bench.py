@@ -408,7 +408,8 @@ def main():
             capi.check(lib.sgl_set_tile_owner_map(None, 0, 0))
             strong = {}
             for key, n_steps in (("c3", 40), ("c4big", 8)):
-                r = bc.measure_case(lib, key, rank, world, "nccl", steps=n_steps, work=os.path.join(ROOT, "build", "bench"))
+                r = bc.measure_case(lib, key, rank, world, "p2p" if store is not None else "nccl", steps=n_steps,
+                                    work=os.path.join(ROOT, "build", "bench"), control_group=ctl)
                 strong[key] = {k: r[k] for k in ("workload", "n_gpus", "units_per_s", "unit", "steps", "ms_per_step", "gfrag_per_s", "parallelism",
                                                  "roofline", "kernel_ms_per_step") if k in r}
         except Exception as e:   # never lose the headline line to the extra block

@@ -144,7 +144,10 @@ __global__ void __launch_bounds__(128) sglVertexKernel(const SglDrawRec *draws) 
     float vary[32];
     clip = sglVertexShader(d, attr, vary);
     float4 *vo = reinterpret_cast<float4 *>(d.varyings + (size_t) v * d.varyingStride);
-    for (int k = 0; k < d.varyingStride / 4; k++) vo[k] = make_float4(vary[4 * k], vary[4 * k + 1], vary[4 * k + 2], vary[4 * k + 3]);
+    const int nq = d.varyingStride / 4;
+#pragma unroll
+    for (int k = 0; k < 8; k++)      // fully unrolled + predicated: constant indices keep vary[] in registers
+      if (k < nq) vo[k] = make_float4(vary[4 * k], vary[4 * k + 1], vary[4 * k + 2], vary[4 * k + 3]);
   }
   reinterpret_cast<float4 *>(d.clipPos)[v] = make_float4(clip.x, clip.y, clip.z, clip.w);
   d.clipMask[v] = sglClipMask(clip);
@@ -153,22 +156,35 @@ __global__ void __launch_bounds__(128) sglVertexKernel(const SglDrawRec *draws) 
 }
 
 // Lazy varyings: the full vertex shader for the vertices the setup kernel marked (SglDrawRec::vertexUsed) -- in a
-// tile-sharded pass a rank needs the varyings of the primitives that reach its own tiles only.  Same grid as the vertex kernel.
+// tile-sharded pass a rank needs the varyings of the primitives that reach its own tiles only.  A thread looks at eight
+// flags with one 8-byte load (the flag array of a draw is 16-byte aligned and padded): grid = (ceil(maxVertices/1024), draws).
+#define SGL_VARYING_PER_THREAD 8
 __global__ void __launch_bounds__(128) sglVaryingKernel(const SglDrawRec *draws) {
   const SglDrawRec &d = draws[blockIdx.y];
-  int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= d.vertexCount || !d.vertexUsed || !d.vertexUsed[v] || d.varyingStride == 0) return;
-  const float4 *src = reinterpret_cast<const float4 *>(d.vertexIn) + (size_t) v * 4;
-  float attr[16];
+  const int v0 = (blockIdx.x * blockDim.x + threadIdx.x) * SGL_VARYING_PER_THREAD;
+  if (v0 >= d.vertexCount || !d.vertexUsed || d.varyingStride == 0) return;
+  const uint2 f = *reinterpret_cast<const uint2 *>(d.vertexUsed + v0);
+  if ((f.x | f.y) == 0u) return;
+#pragma unroll 1
+  for (int k = 0; k < SGL_VARYING_PER_THREAD; k++) {
+    const uint32_t w = k < 4 ? f.x : f.y;
+    if (!((w >> (8 * (k & 3))) & 0xffu) || v0 + k >= d.vertexCount) continue;
+    const int v = v0 + k;
+    const float4 *src = reinterpret_cast<const float4 *>(d.vertexIn) + (size_t) v * 4;
+    float attr[16];
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    float4 q = __ldg(src + i);
-    attr[4 * i] = q.x; attr[4 * i + 1] = q.y; attr[4 * i + 2] = q.z; attr[4 * i + 3] = q.w;
+    for (int i = 0; i < 4; i++) {
+      float4 q = __ldg(src + i);
+      attr[4 * i] = q.x; attr[4 * i + 1] = q.y; attr[4 * i + 2] = q.z; attr[4 * i + 3] = q.w;
+    }
+    float vary[32];
+    sglVertexShader(d, attr, vary);
+    float4 *vo = reinterpret_cast<float4 *>(d.varyings + (size_t) v * d.varyingStride);
+    const int nq = d.varyingStride / 4;
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (q < nq) vo[q] = make_float4(vary[4 * q], vary[4 * q + 1], vary[4 * q + 2], vary[4 * q + 3]);
   }
-  float vary[32];
-  sglVertexShader(d, attr, vary);
-  float4 *vo = reinterpret_cast<float4 *>(d.varyings + (size_t) v * d.varyingStride);
-  for (int k = 0; k < d.varyingStride / 4; k++) vo[k] = make_float4(vary[4 * k], vary[4 * k + 1], vary[4 * k + 2], vary[4 * k + 3]);
 }
 
 // grid = (ceil(maxInputPrims/128), drawCount)
@@ -340,14 +356,34 @@ __global__ void __launch_bounds__(256) sglBinFillKernel(SglPassParams P) {
   int tx0, ty0, tx1, ty1;
   if (!sglPrimTiles(p, P.fbW, P.fbH, tx0, ty0, tx1, ty1)) return;
   if (p.flags & SGL_PF_BIG) return;     // lives in the pass-wide big list (bigCapacity >= primSlots, never overflows)
-  for (int ty = ty0; ty <= ty1; ty++)
-    for (int tx = tx0; tx <= tx1; tx++) {
-      int t = ty * P.tilesX + tx;
-      if (P.tileOwner && P.tileOwner[t] != P.rank) continue;
-      if (!sglPrimNearTile(p, tx, ty)) continue;
-      uint32_t pos = P.tileOffset[t] + atomicAdd(&P.tileCursor[t], 1u);
-      P.binSlots[pos] = (uint32_t) slot;   // pos < binCapacity: the setup kernel reserved every entry it counted
+  // <= SGL_BIG_PRIM_TILES (64) tiles: first the set of tiles as a bit mask, then the cursor atomics four at a time -- the
+  // returned positions are needed for the stores only, so four round trips overlap instead of one per tile in sequence
+  const int w = tx1 - tx0 + 1, n = w * (ty1 - ty0 + 1);
+  unsigned long long m = 0ull;
+  for (int k = 0; k < n && k < 64; k++) {
+    const int tx = tx0 + k % w, ty = ty0 + k / w, t = ty * P.tilesX + tx;
+    if (P.tileOwner && P.tileOwner[t] != P.rank) continue;
+    if (sglPrimNearTile(p, tx, ty)) m |= 1ull << k;
+  }
+  while (m) {
+    int t[4];
+    uint32_t c[4], o[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      t[q] = -1;
+      if (m) {
+        const int k = __ffsll((long long) m) - 1;
+        m &= m - 1ull;
+        t[q] = (ty0 + k / w) * P.tilesX + tx0 + k % w;
+      }
     }
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (t[q] >= 0) { c[q] = atomicAdd(&P.tileCursor[t[q]], 1u); o[q] = P.tileOffset[t[q]]; }
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (t[q] >= 0) P.binSlots[o[q] + c[q]] = (uint32_t) slot;   // < binCapacity: the setup kernel reserved every entry it counted
+  }
 }
 
 #endif  // SGL_RASTER_ONLY

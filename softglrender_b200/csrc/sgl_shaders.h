@@ -83,12 +83,14 @@ SGL_HD V4 sglVertexShader(const SglDrawRec &d, const float *vin, float *vout) {
     case SGL_SHADER_BASIC:            // BasicSoft.h:66-69
       return pos;
     case SGL_SHADER_FXAA: {           // FxaaSoft.h:58-61: gl_Position = vec4(a_position, 1)
+#pragma unroll
       for (int i = 0; i < 8; i++) vout[i] = 0.f;
       vout[0] = vin[4];
       vout[1] = vin[5];
       return v4(px, py, pz, 1.0f);
     }
     case SGL_SHADER_SKYBOX: {         // SkyboxSoft.h:67-76: pos.xyww, z = 0 when reverseZ
+#pragma unroll
       for (int i = 0; i < 8; i++) vout[i] = 0.f;
       vout[0] = px; vout[1] = py; vout[2] = pz;
       V4 r = v4(pos.x, pos.y, pos.w, pos.w);
@@ -97,6 +99,7 @@ SGL_HD V4 sglVertexShader(const SglDrawRec &d, const float *vin, float *vout) {
     }
     case SGL_SHADER_IBL_IRRADIANCE:   // IBLIrradianceSoft.h:62-67
     case SGL_SHADER_IBL_PREFILTER: {  // IBLPrefilterSoft.h:69-74: Position.z = pos.w
+#pragma unroll
       for (int i = 0; i < 8; i++) vout[i] = 0.f;
       vout[0] = px; vout[1] = py; vout[2] = pz;
       return v4(pos.x, pos.y, pos.w, pos.w);
@@ -105,6 +108,7 @@ SGL_HD V4 sglVertexShader(const SglDrawRec &d, const float *vin, float *vout) {
   }
   // BlinnPhongSoft.h:103-121 / PbrSoft.h:110-127
   bool bp = d.shader == SGL_SHADER_BLINNPHONG;
+#pragma unroll
   for (int i = 0; i < 32; i++) vout[i] = 0.f;
   const float *model = uMat(d, 16);
   vout[0] = vin[4];
@@ -117,19 +121,23 @@ SGL_HD V4 sglVertexShader(const SglDrawRec &d, const float *vin, float *vout) {
   V3 cam = uV3(d, 272), light = uV3(d, 288);
   vout[12] = cam.x - wp.x; vout[13] = cam.y - wp.y; vout[14] = cam.z - wp.z;
   vout[16] = light.x - wp.x; vout[17] = light.y - wp.y; vout[18] = light.z - wp.z;
-  int nOff = 20;
   if (bp) {
     V4 sp = xMat4MulPoint(uMat(d, 192), px, py, pz);
     vout[20] = sp.x; vout[21] = sp.y; vout[22] = sp.z; vout[23] = sp.w;
-    nOff = 24;
   }
   if (d.defines & SGL_DEF_NORMAL_MAP) {
     const float *it = uMat(d, 144);
     V3 N = normalize(sglMat3MulCols(it, it + 4, it + 8, nrm));
     V3 T = normalize(sglMat3MulCols(it, it + 4, it + 8, v3(vin[12], vin[13], vin[14])));
     V3 T2 = normalize(T - dot(T, N) * N);
-    vout[nOff] = N.x; vout[nOff + 1] = N.y; vout[nOff + 2] = N.z;
-    vout[nOff + 4] = T2.x; vout[nOff + 5] = T2.y; vout[nOff + 6] = T2.z;
+    // constant indices in both arms: the varyings of a thread stay in registers (a runtime offset sends the array to local memory)
+    if (bp) {
+      vout[24] = N.x; vout[25] = N.y; vout[26] = N.z;
+      vout[28] = T2.x; vout[29] = T2.y; vout[30] = T2.z;
+    } else {
+      vout[20] = N.x; vout[21] = N.y; vout[22] = N.z;
+      vout[24] = T2.x; vout[25] = T2.y; vout[26] = T2.z;
+    }
   }
   return pos;
 }

@@ -145,7 +145,7 @@ struct SglPassParams {
   uint32_t *tileSortedCount;    // [tiles] entries of the sorted list, SGL_TILE_UNSORTED = use the in-kernel gather
   uint32_t *tileOrder;          // [SGL_TILE_CLASSES][tiles]: tiles by descending list length class (heavy tiles are
   uint32_t *tileClassCount;     // [SGL_TILE_CLASSES]           launched first so that they cannot become stragglers)
-  int32_t splitCap;             // MSAA visibility kernel: up to splitCap heavy tiles run as four quarter-tile CTAs
+  int32_t splitCap;             // visibility kernel: up to splitCap heavy tiles run as four quarter-tile CTAs
   // big primitives (> SGL_BIG_PRIM_TILES tiles in their pixel range, or the bins were exhausted when they arrived): the
   // setup kernel lists them in bigAll; sglBigBinKernel bins them tile by tile like everybody else.  Only what does not fit
   // the bins then stays in the RESIDUAL list bigList/bigCount, which every tile kernel scans (normally empty).

@@ -122,6 +122,14 @@ __device__ __forceinline__ void sglSortTileList(uint32_t *keys, uint32_t *vals, 
   sglBitonicSortKV(keys, vals, n2);
 }
 
+// How many heavy tiles run as four quarter-tile items (splitCap = 0: none).  MSAA: the first splitCap of them.  One sample per
+// pixel: all of them while they fit splitCap (few heavy tiles = stragglers), none otherwise (mostly heavy tiles = throughput).
+__device__ __forceinline__ uint32_t sglVisSplitCount(const SglPassParams &P, uint32_t heavyTiles) {
+  const uint32_t cap = (uint32_t) P.splitCap;
+  if (P.samples == 1) return heavyTiles <= cap ? heavyTiles : 0u;
+  return heavyTiles < cap ? heavyTiles : cap;
+}
+
 // Geometry-stage preparation of the pixel stage's input: one WARP per tile (in heavy-first work order) sorts the tile's bin
 // by order key and writes (a) the sorted slots (tileSorted, read by the fused kernel), (b) the tile's packed record STREAM:
 // 128-byte entries {primitive record, edge constants, slot} in submission order, contiguous, so that the visibility kernel
@@ -158,7 +166,7 @@ __global__ void __launch_bounds__(32 * SGL_TILE_SORT_WARPS) sglTileSortKernel(Sg
   const uint32_t o = (uint32_t) (blockIdx.x * SGL_TILE_SORT_WARPS + warp);
   if (o >= owned) return;
   const uint32_t heavyTiles = cnt[0] + cnt[1];
-  const uint32_t split = heavyTiles < (uint32_t) P.splitCap ? heavyTiles : (uint32_t) P.splitCap;   // splitCap = 0: no quarter items
+  const uint32_t split = sglVisSplitCount(P, heavyTiles);
   const uint32_t ctaItems = 4u * split + (heavyTiles - split);
   int tile = -1;
   {
@@ -323,6 +331,26 @@ __device__ __forceinline__ void sglVisSamplePrim(const SglPassParams &P, const S
   if (wrote & 1u) owner = sglOwner(slot, 0);
 }
 
+// Single-sample triangle against one pixel WITHOUT the depth test: the part of sglCoverTriangle<1> / sglVisPixelPrim<1> that
+// does not depend on what earlier primitives left in the pixel.  Returns "covered"; z = the clamped depth the test and the
+// write use (one sample per pixel: no depth-range clipping, RendererSoft.cpp:797,871-874).
+__device__ __forceinline__ bool sglVisEvalTriangle1(const SglPassParams &P, const SglVisPrim &vp, int px, int py, float &z) {
+  const SglPrim &p = vp.p;
+  if (px < p.bx0 || px > p.bx1 || py < p.by0 || py > p.by1) return false;
+  if (p.flags & SGL_PF_IRREGULAR) {
+    const SglDrawRec &d = P.draws[p.draw];
+    int q;
+    if (!sglAxisVisitedExact(min3f(p.v[0][0], p.v[1][0], p.v[2][0]), max3f(p.v[0][0], p.v[1][0], p.v[2][0]), d.vpW, px, q)) return false;
+    if (!sglAxisVisitedExact(min3f(p.v[0][1], p.v[1][1], p.v[2][1]), max3f(p.v[0][1], p.v[1][1], p.v[2][1]), d.vpH, py, q)) return false;
+  }
+  const float fx = (float) px, fy = (float) py;
+  if (sglTriSurelyOutside(vp.e, fx + 0.5f, fy + 0.5f, 0.f, 0.f)) return false;
+  float b0, b1, b2;
+  if (!sglBarycentric(vp.e, xadd(0.5f, fx), xadd(0.5f, fy), b0, b1, b2)) return false;
+  z = gclamp(sglInterpZ(p, 2, b0, b1, b2), 0.f, 1.f);
+  return true;
+}
+
 // one primitive against one pixel: coverage + depth, owners instead of colours
 template<int NS>
 __device__ __forceinline__ void sglVisPixelPrim(const SglPassParams &P, const SglVisPrim &vp, uint32_t slot, int px, int py,
@@ -377,7 +405,7 @@ __device__ __forceinline__ void sglVisWorkCounts(const SglPassParams &P, uint32_
 #pragma unroll
   for (int c = 0; c < SGL_TILE_CLASSES; c++) cnt[c] = P.tileClassCount[c];
   heavy = cnt[0] + cnt[1];
-  split = heavy < (uint32_t) P.splitCap ? heavy : (uint32_t) P.splitCap;
+  split = sglVisSplitCount(P, heavy);
   ctaItems = 4u * split + (heavy - split);
   allItems = ctaItems + cnt[2] + cnt[3];
 }
@@ -424,9 +452,11 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS, SGL_VIS_MIN_BLOCKS) sglVisKe
   const bool hasColor = P.colorBase != nullptr, hasDepth = P.depthBase != nullptr;
   const int tx = tile % P.tilesX, ty = tile / P.tilesX;
 
-  // ---- pixel state (registers): one pixel per lane (a warp owns an 8x4 block), or -- quarter items -- one sample per
-  //      lane (a warp owns a 4x2 block, depth[0] / owner[0] only)
-  const bool quarterMode = NS == 4 && wk.quarter != 0xFFFFFFFFu;
+  // ---- pixel state (registers): one pixel per lane (a warp owns an 8x4 block), or -- quarter items -- four lanes per pixel
+  //      (a warp owns a 4x2 block, depth[0] / owner[0] only): with MSAA each of the four lanes owns one SAMPLE; with one sample
+  //      per pixel the four lanes hold the same state and evaluate four consecutive surviving triangles at once, whose
+  //      results are then applied in submission order (the depth test is the only step that depends on the order)
+  const bool quarterMode = wk.quarter != 0xFFFFFFFFu;
   int wbx, wby, px, py, smp = 0;
   if (quarterMode) {
     wbx = tx * SGL_TILE + (int) (wk.quarter & 1u) * 8 + (warp & 1) * 4;
@@ -447,7 +477,7 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS, SGL_VIS_MIN_BLOCKS) sglVisKe
 #pragma unroll
   for (int s = 0; s < NS; s++) { depth[s] = P.clearDepth; owner[s] = SGL_OWNER_NONE; }
   if (inFb && hasDepth && !P.clearDepthFlag) {
-    if (quarterMode) depth[0] = P.depthBase[pix * 4 + smp];
+    if (quarterMode) depth[0] = NS == 4 ? P.depthBase[pix * 4 + smp] : P.depthBase[pix];
     else if (NS == 4) {
       float4 dq = reinterpret_cast<const float4 *>(P.depthBase)[pix];
       depth[0] = dq.x; depth[NS > 1 ? 1 : 0] = dq.y; depth[NS > 2 ? 2 : 0] = dq.z; depth[NS > 3 ? 3 : 0] = dq.w;
@@ -512,6 +542,33 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS, SGL_VIS_MIN_BLOCKS) sglVisKe
       wNear = __uint_as_float(__reduce_min_sync(0xffffffffu, lo));
     };
     if (hiz) blockDepthRange();
+    // single-sample quarter items: survivors wait in `pack` (8 bits each) until four triangles are there
+    uint32_t pack = 0;
+    int g = 0;
+    auto runGroup = [&]() {
+      if (g == 0) return;
+      bool in = false;
+      float z = 0.f;
+      if (smp < g && inFb) in = sglVisEvalTriangle1(P, recs[(pack >> (8 * smp)) & 0xffu], px, py, z);
+      bool wroteDepth = false;
+      for (int j = 0; j < g; j++) {                      // g is warp-uniform
+        const int srcLane = (lane & 28) | j;
+        const bool inj = __shfl_sync(0xffffffffu, in ? 1 : 0, srcLane) != 0;
+        const float zj = __shfl_sync(0xffffffffu, z, srcLane);
+        const SglVisPrim &vj = recs[(pack >> (8 * j)) & 0xffu];
+        const uint32_t fl = vj.p.flags;
+        wroteDepth = wroteDepth || ((fl & SGL_PF_DEPTH_TEST) && (fl & SGL_PF_DEPTH_MASK));
+        if (!inj) continue;
+        if (fl & SGL_PF_DEPTH_TEST) {
+          if (!hasDepth || !sglDepthTest(zj, depth[0], (fl >> SGL_PF_DEPTH_FUNC_SHIFT) & 7)) continue;
+          if (fl & SGL_PF_DEPTH_MASK) depth[0] = zj;
+        }
+        owner[0] = sglOwner(vj.slot, 0);
+      }
+      pack = 0;
+      g = 0;
+      if (hiz && wroteDepth) blockDepthRange();
+    };
 #pragma unroll
     for (int hh = 0; hh < 2; hh++) {
       uint32_t m = rel[hh];
@@ -523,11 +580,20 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS, SGL_VIS_MIN_BLOCKS) sglVisKe
           const uint32_t f = (recs[k].p.flags >> SGL_PF_DEPTH_FUNC_SHIFT) & 7u;
           if ((f == 1u && zb >= wFar) || (f == 3u && zb > wFar) || (f == 4u && zb <= wNear) || (f == 6u && zb < wNear)) continue;
         }
+        if (NS == 1 && quarterMode) {
+          if ((recs[k].p.flags & SGL_PF_KIND_MASK) == SGL_PK_TRIANGLE) {
+            pack |= (uint32_t) k << (8 * g);
+            if (++g == 4) runGroup();
+            continue;
+          }
+          runGroup();      // a point / line: in order after the triangles before it; the four lanes of a pixel do the same work
+        }
         if (NS == 4 && quarterMode) sglVisSamplePrim(P, recs[k], recs[k].slot, px, py, smp, lane, inFb, depth[0], owner[0], hasColor, hasDepth);
         else if (inFb) sglVisPixelPrim<NS>(P, recs[k], recs[k].slot, px, py, depth, owner, hasColor, hasDepth);
         if (hiz && (recs[k].p.flags & SGL_PF_DEPTH_MASK)) blockDepthRange();
       }
     }
+    if (NS == 1 && quarterMode) runGroup();
   };
 
   if (streamed) {
@@ -618,9 +684,14 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS, SGL_VIS_MIN_BLOCKS) sglVisKe
   }
 
   if (inFb) {
-    if (quarterMode) {
+    if (quarterMode && NS == 4) {
       if (hasDepth) P.depthBase[pix * 4 + smp] = depth[0];
       if (hasColor) P.vis[pix * 4 + smp] = owner[0];
+    } else if (quarterMode) {
+      if (smp == 0) {      // the four lanes of the pixel hold the same state
+        if (hasDepth) P.depthBase[pix] = depth[0];
+        if (hasColor) P.vis[pix] = owner[0];
+      }
     } else {
       if (hasDepth) {
         if (NS == 4) reinterpret_cast<float4 *>(P.depthBase)[pix] =

@@ -45,6 +45,8 @@ struct TextureRec {
   bool rbPending = false;         // a later pass that overwrites the colour image must wait for rbDone on the device
 };
 
+#define SGL_ARENAS 8
+#define SGL_SMALL_ARENA_BYTES ((size_t) 32 << 20)
 struct Ctx {
   bool ready = false;
   int refs = 0;              // sgl_init calls not yet matched by sgl_shutdown (several Renderer objects may share the context)
@@ -78,14 +80,16 @@ struct Ctx {
     void *stagingHost = nullptr;   // pinned: this slot's draw records (fixed address: the geometry graph's copy node reads it)
     size_t stagingCap = 0;
   };
-  Arena arenas[3];
+  // small passes (arena <= SGL_SMALL_ARENA_BYTES) rotate over all SGL_ARENAS slots, large ones over the first three: many
+  // small dependent kernels per pass (config 5: 512x512 views) need more passes in flight to hide the geometry chain's latency
+  Arena arenas[SGL_ARENAS];
   int arenaNext = 0;
   unsigned long long *dTileTimes = nullptr;        // sgl_debug_tile_times
   size_t tileTimesCap = 0;
   int tileTiming = 0;
   const uint32_t *lastTileSortedCount = nullptr;   // of the most recent non-depth-only pass (instrumentation)
   int lastTilesX = 0, lastTilesY = 0;
-  cudaStream_t geomStreams[3] = {nullptr, nullptr, nullptr};   // one per arena slot: geometry stages of consecutive passes are independent
+  cudaStream_t geomStreams[SGL_ARENAS] = {};   // one per arena slot: geometry stages of consecutive passes are independent
   // depth-only passes (shadow maps) run their pixel stage on an auxiliary stream: they start when all earlier pixel work
   // is done and only the next kernel that SAMPLES textures (or touches their depth texture) waits for them, so the
   // shadow pass of a frame overlaps the visibility kernel of its main pass
@@ -98,6 +102,8 @@ struct Ctx {
   int noOverlap = 0;           // SGL_NO_OVERLAP=1: geometry and pixel stages on one stream (A/B runs)
   int noPassSplit = 0;         // SGL_NO_PASS_SPLIT=1: a pass with a blended tail runs entirely in the fused kernel (A/B runs)
   int noLazyVaryings = 0;      // SGL_NO_LAZY_VARYINGS=1: tile-sharded passes shade every vertex up front (A/B runs)
+  int fewArenas = 0;           // SGL_FEW_ARENAS=1: three arena slots for every pass (A/B runs)
+  int noSplit1 = 0;            // SGL_NO_SPLIT1=1: single-sample heavy tiles are not split (A/B runs)
   int noSplit = 0;             // SGL_NO_SPLIT=1: heavy MSAA tiles are not split into quarter-tile CTAs (A/B runs)
   void *dummyTexels = nullptr; // backing store of texture table entry 0
   uint32_t *vis = nullptr;     // visibility buffer of the deferred path
@@ -507,6 +513,10 @@ int sgl_init(int device_ordinal, int rank, int world) {
     g.noPassSplit = (nps && atoi(nps) != 0) ? 1 : 0;
     const char *ns = getenv("SGL_NO_SPLIT");
     g.noSplit = (ns && atoi(ns) != 0) ? 1 : 0;
+    const char *fa = getenv("SGL_FEW_ARENAS");
+    g.fewArenas = (fa && atoi(fa) != 0) ? 1 : 0;
+    const char *ns1 = getenv("SGL_NO_SPLIT1");
+    g.noSplit1 = (ns1 && atoi(ns1) != 0) ? 1 : 0;
     const char *nl = getenv("SGL_NO_LAZY_VARYINGS");
     g.noLazyVaryings = (nl && atoi(nl) != 0) ? 1 : 0;
   }
@@ -1171,7 +1181,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     oVout[i] = take((size_t) std::max(extraVerts, 1) * 64);
     oVary[i] = take((size_t) r.vertexCap * std::max(r.varyingStride, 1) * 4);
     oUsed[i] = usedBytes;
-    if (lazyVaryings) usedBytes = alignUp(usedBytes + (size_t) r.vertexCount, 16);
+    if (lazyVaryings) usedBytes = alignUp(usedBytes + (size_t) r.vertexCount, 16);     // sglVaryingKernel reads 8 flags at a time
     g.hostVertices += (unsigned long long) r.vertexCount;
     g.hostIndices += (unsigned long long) r.indexCount;
     maxVerts = std::max(maxVerts, r.vertexCount);
@@ -1195,15 +1205,21 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   size_t oTileSortedCount = depthOnly ? 0 : take(sizeof(uint32_t) * nTiles);
   size_t oTileOrder = depthOnly ? 0 : take(sizeof(uint32_t) * nTiles * SGL_TILE_CLASSES);
   // visibility-kernel work items (heavy MSAA tiles: four quarter items) and the packed per-tile record streams
-  const int splitCap = (!depthOnly && samples == 4 && !g.noSplit) ? std::max(nTiles / 4, 1) : 0;
+  // heavy tiles (>= 40 entries) run as four quarter-tile CTAs.  MSAA: one sample per lane, at most a quarter of the tiles.
+  // One sample per pixel: four triangles per pixel at a time -- this shortens the longest tiles when FEW tiles are heavy (a
+  // model in front of a floor: the kernel ends with its stragglers); when most tiles are heavy (config 4's triangle soup) the
+  // kernel is throughput-bound and four CTAs culling the same list are a loss, so nothing is split once more than an eighth
+  // of the tiles is heavy (sglVisSplitCount)
+  const int splitCap = (!depthOnly && !g.noSplit) ? (samples == 4 ? std::max(nTiles / 4, 1) : (g.noSplit1 ? 0 : std::max(nTiles / 8, 1))) : 0;
   const size_t streamCapacity = depthOnly ? 0 : std::min<size_t>((size_t) 2 * std::max(primSlots, 1) + (size_t) 16 * nTiles, binCapacity);
   size_t oWork = depthOnly ? 0 : take(sizeof(SglVisWork) * ((size_t) nTiles + 3 * (size_t) splitCap));
   size_t oStream = depthOnly ? 0 : take((size_t) 128 * std::max<size_t>(streamCapacity, 1));
   SecTimer sec(6);
   auto section = [&](int k) { sec.switchTo(k); };
-  Ctx::Arena &arena = g.arenas[g.arenaNext];
-  const cudaStream_t geomStream = g.geomStreams[g.arenaNext];
-  g.arenaNext = (g.arenaNext + 1) % 3;
+  const int arenaSlot = g.arenaNext % (off <= SGL_SMALL_ARENA_BYTES && !g.fewArenas ? SGL_ARENAS : 3);
+  Ctx::Arena &arena = g.arenas[arenaSlot];
+  const cudaStream_t geomStream = g.geomStreams[arenaSlot];
+  g.arenaNext = (g.arenaNext + 1) % (SGL_ARENAS * 3);
   int rc = ensureArena(arena, off);
   if (rc) return rc;
   uint8_t *A = arena.mem;
@@ -1421,7 +1437,8 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
         r2 = launch("sglSetupKernel", sglSetupKernel, dim3((maxPrims + 127) / 128, nDraws), dim3(128), P.draws, so, ss, dt ? 1 : 0);
         if (r2) return r2;
         if (lazyVaryings && maxVerts > 0) {
-          r2 = launch("sglVaryingKernel", sglVaryingKernel, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws);
+          r2 = launch("sglVaryingKernel", sglVaryingKernel, dim3((maxVerts + 128 * SGL_VARYING_PER_THREAD - 1) / (128 * SGL_VARYING_PER_THREAD), nDraws),
+                      dim3(128), P.draws);
           if (r2) return r2;
         }
       }

@@ -33,7 +33,7 @@ def case_table(work, rank, world):
     }
 
 
-def measure_case(lib, key, rank, world, gather_mode="nccl", steps=None, cpu=False, keep_trace=False, work=None, control_group=None):
+def measure_case(lib, key, rank, world, gather_mode="nccl", steps=None, cpu=False, keep_trace=False, work=None, control_group=None, as_rank=None):
     """One secondary workload on `world` GPUs (torch.distributed already initialised by the caller when world > 1; the
     library must run on torch's current stream).  c3 / c4*: ONE frame sharded by screen tiles, owned tiles gathered to rank 0
     inside the timed region (strong scaling); c5: views dealt to the ranks.  Returns the result dict (same on every rank)."""
@@ -59,6 +59,14 @@ def measure_case(lib, key, rank, world, gather_mode="nccl", steps=None, cpu=Fals
     p.setup()
     tex = p.texture_handle("color") if key != "c5" else p.texture_handle("color_v0")
     gather = store = None
+    if as_rank and world == 1 and shard:
+        # one GPU renders the share of rank r of n (no exchange): what one rank of a tile-sharded run does, without n GPUs
+        w_, h_ = C.c_int(), C.c_int()
+        capi.check(lib.sgl_texture_level_size(tex, 0, C.byref(w_), C.byref(h_)))
+        capi.check(lib.sgl_set_rank(as_rank[0], as_rank[1]))
+        gather = M.TileGather(w_.value, h_.value, as_rank[0], as_rank[1], shard)
+        gather.install(lib)
+        gather_mode = "none"
     if world > 1 and shard:
         w_, h_ = C.c_int(), C.c_int()
         capi.check(lib.sgl_texture_level_size(tex, 0, C.byref(w_), C.byref(h_)))
@@ -134,6 +142,8 @@ def measure_case(lib, key, rank, world, gather_mode="nccl", steps=None, cpu=Fals
             store.close()
     if gather is not None:
         capi.check(lib.sgl_set_tile_owner_map(None, 0, 0))
+    if as_rank and world == 1:
+        capi.check(lib.sgl_set_rank(0, 1))
     p.close()
     os.environ.pop("SGL_TEXTURE_LAYOUT", None)
     os.environ.pop("SGL_SHARD_HALO", None)
@@ -148,6 +158,8 @@ def measure_case(lib, key, rank, world, gather_mode="nccl", steps=None, cpu=Fals
          "clip_overflow": ctr["clip_overflow"], "bin_spills": ctr["bin_spills"], "host_us_pass_end_per_step": ctr["host_ns_pass_end"] / 1e3 / steps,
          "host_us_draw_per_step": ctr["host_ns_draw"] / 1e3 / steps, "passes_per_step": ctr["passes"] / steps, "draws_per_step": ctr["draws"] / steps,
          "kernel_ms_per_step": {k: v[1] / 3.0 for k, v in sorted(kt.items())}}
+    if as_rank and world == 1 and shard:
+        r["parallelism"] = "one GPU rendering the tiles of rank %d of %d (%s), no exchange" % (as_rank[0], as_rank[1], shard)
     if world > 1:
         r["parallelism"] = ("view-parallel, no exchange (every view stays in the HBM of the rank that rendered it)" if key == "c5" else
                             "one frame sharded by screen tiles (%s), geometry replicated, owned tiles gathered to rank 0 by %s inside the timed region"
@@ -180,7 +192,9 @@ def main():
     ap.add_argument("--only", default="c1,c3,c4,c4big,c5")
     ap.add_argument("--out", default="")
     ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p", "none"], help="N > 1, tile-sharded configs: how owned tiles reach rank 0")
+    ap.add_argument("--as-rank", default="", help="R/N on one GPU: render only the tiles rank R of N owns (what one rank of a sharded run does)")
     args = ap.parse_args()
+    as_rank = tuple(int(x) for x in args.as_rank.split("/")) if args.as_rank else None
     rank, local, world = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     from softglrender_b200 import capi
     dist = None
@@ -198,7 +212,7 @@ def main():
         capi.check(lib.sgl_set_stream(C.c_void_p(stream.cuda_stream)))
     results = {}
     for key in args.only.split(","):
-        r = measure_case(lib, key, rank, world, args.gather, cpu=args.cpu, control_group=ctl)
+        r = measure_case(lib, key, rank, world, args.gather, cpu=args.cpu, control_group=ctl, as_rank=as_rank)
         results[key] = r
         if rank == 0:
             print(key, json.dumps(r), flush=True)

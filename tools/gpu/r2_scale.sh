@@ -5,7 +5,7 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 mkdir -p gpurun_out
 $TR bench.py --gpus $N --steps 500 --warmup 50 > gpurun_out/r02_bench_n${N}_frames.json 2> gpurun_out/r02_bench_n${N}_frames.err
 $TR bench.py --gpus $N --steps 300 --warmup 30 --mgpu tiles --no-strong > gpurun_out/r02_bench_n${N}_tiles.json 2> gpurun_out/r02_bench_n${N}_tiles.err
-$TR tools/bench_configs.py --only ${2:-c3,c4big,c5} --out gpurun_out/r02_configs_n${N}.json > gpurun_out/r02_configs_n${N}.log 2>&1
+$TR tools/bench_configs.py --gather ${3:-p2p} --only ${2:-c3,c4big,c5} --out gpurun_out/r02_configs_n${N}.json > gpurun_out/r02_configs_n${N}.log 2>&1
 python - <<PY
 import json
 for f in ("frames", "tiles"):
