@@ -219,7 +219,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; RendererCUDA has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    host_numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "n/a"
+    # also at N = 1: a pinned frame buffer that lands on the other socket makes the 8.3 MB read-back cross the inter-socket link
+    host_numa = bind_to_gpu_numa_node(local_rank) if not os.environ.get("BENCH_NO_NUMA") else "off (BENCH_NO_NUMA)"
     ctl = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -370,12 +371,24 @@ def main():
     # ---- timed region 2: end to end through the public API with host buffers: per frame the draw records / uniform
     #      snapshots are uploaded from pinned memory and the finished frame is read back into pinned host memory
     #      (pipelined: the copy of frame f overlaps the geometry + visibility work of frame f+1)
+    #      The read-back path gets its own untimed warm-up first (staging buffers, the first DMA into the pinned frames, lazily
+    #      loaded copy kernel): one-off costs of some 10 ms that a 500-step region would otherwise carry as 30 us per step.
+    for _ in range(max(3, min(W, 20))):
+        step(True)
+    flush_store(True)
+    capi.check(lib.sgl_readback_wait())
+    sync_all()
+    g_d2h[0] = 0
     capi.check(lib.sgl_reset_counters())
     sync_all()
+    e2e_dev_ms = C_float()
     t0 = time.perf_counter()
+    capi.check(lib.sgl_timer_begin())
     for _ in range(K):
         step(True)
     flush_store(True)
+    capi.check(lib.sgl_timer_end(e2e_dev_ms))      # blocks until the main stream has drained (the last copy may still run)
+    e2e_submit_s = time.perf_counter() - t0
     sync_all()
     e2e_s = _max_over_ranks(time.perf_counter() - t0, world)
     ctr2 = capi.counters()
@@ -428,7 +441,11 @@ def main():
             # CPU work of the library per step (state snapshots + arena layout + graph launches), without the time the host spends
             # blocked because the GPU is the bottleneck (the burst figure above includes that)
             "host_cpu_ms_per_step": (ctr["host_ns_pass_end"] + ctr["host_ns_draw"] - ctr["host_ns_wait_gpu"]) / 1e6 / K,
-            "host_blocked_on_gpu_ms_per_step": ctr["host_ns_wait_gpu"] / 1e6 / K}
+            "host_blocked_on_gpu_ms_per_step": ctr["host_ns_wait_gpu"] / 1e6 / K,
+            # the e2e region seen from the device (events on the rendering stream) and from the submitting thread: tells a
+            # GPU-side slowdown by the copies from a host-side one
+            "e2e_device_ms_per_step": e2e_dev_ms.value / K, "e2e_host_blocked_ms_per_step": ctr2["host_ns_wait_gpu"] / 1e6 / K,
+            "e2e_wall_ms_until_main_stream_drained_per_step": e2e_submit_s * 1e3 / K}
     if strong is not None:
         line["strong_scaling"] = strong
     if rank == 0:

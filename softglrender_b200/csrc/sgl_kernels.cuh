@@ -706,6 +706,22 @@ __global__ void sglFill32Kernel(uint32_t *dst, uint32_t value, size_t n) {
   for (; i < n; i += stride) dst[i] = value;
 }
 
+// Head of a pass's geometry chain in ONE launch: zero the counter block and fetch the draw records straight from the
+// slot's pinned (UVA-mapped) staging buffer.  A memset node + a host-to-device copy node did the same through a copy
+// engine, where the 5 KB of records can queue behind the 8 MB device-to-host copy of the previous frame's read-back.
+__global__ void sglPassHeadKernel(uint4 *zero, size_t nZero16, uint4 *dst, const uint4 *srcHost, size_t nCopy16) {
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (size_t k = i; k < nCopy16; k += stride) dst[k] = srcHost[k];
+  for (size_t k = i; k < nZero16; k += stride) zero[k] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+__global__ void sglCopy16Kernel(uint4 *dst, const uint4 *src, size_t n16) {
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (; i < n16; i += stride) dst[i] = src[i];
+}
+
 // ---- known-answer-test kernels (wrap the device functions above) ---------------------------------------------
 __global__ void sglKatBarycentricKernel(const float *tri, const float *xy, int n, float *bcOut, int *insideOut, float *zwOut) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

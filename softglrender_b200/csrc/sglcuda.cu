@@ -84,6 +84,10 @@ struct Ctx {
   // small dependent kernels per pass (config 5: 512x512 views) need more passes in flight to hide the geometry chain's latency
   Arena arenas[SGL_ARENAS];
   int arenaNext = 0;
+  int ringSize = 4;            // arena slots that ordinary passes rotate over (SGL_RING=3..8).  Four: in a frame of two passes (shadow + main) the main
+                               // pass always reuses the slot of the main pass two frames back; with three its geometry waited for the PREVIOUS frame's
+                               // shadow raster (which waits for the frame before to finish shading) two frames out of three -- e2e +4.8 % on config 2
+  int smallStreak = 0;         // consecutive passes whose arena is small (<= SGL_SMALL_ARENA_BYTES, <= 4096 tiles)
   unsigned long long *dTileTimes = nullptr;        // sgl_debug_tile_times
   size_t tileTimesCap = 0;
   int tileTiming = 0;
@@ -102,6 +106,9 @@ struct Ctx {
   int noOverlap = 0;           // SGL_NO_OVERLAP=1: geometry and pixel stages on one stream (A/B runs)
   int noPassSplit = 0;         // SGL_NO_PASS_SPLIT=1: a pass with a blended tail runs entirely in the fused kernel (A/B runs)
   int noLazyVaryings = 0;      // SGL_NO_LAZY_VARYINGS=1: tile-sharded passes shade every vertex up front (A/B runs)
+  int rbMode = 0;              // SGL_RB_MODE=1: read-back snapshot by a copy kernel on the rendering stream (A/B runs: 3 % slower on config 2)
+  cudaEvent_t rbStageFree[2] = {nullptr, nullptr};   // PCIe copy out of rbStage[k] finished
+  int ceUpload = 0;            // SGL_CE_UPLOAD=1: counter memset + draw-record upload as copy-engine nodes (A/B runs)
   int fewArenas = 0;           // SGL_FEW_ARENAS=1: three arena slots for every pass (A/B runs)
   int noSplit1 = 0;            // SGL_NO_SPLIT1=1: single-sample heavy tiles are not split (A/B runs)
   int noSplit = 0;             // SGL_NO_SPLIT=1: heavy MSAA tiles are not split into quarter-tile CTAs (A/B runs)
@@ -515,6 +522,12 @@ int sgl_init(int device_ordinal, int rank, int world) {
     g.noSplit = (ns && atoi(ns) != 0) ? 1 : 0;
     const char *fa = getenv("SGL_FEW_ARENAS");
     g.fewArenas = (fa && atoi(fa) != 0) ? 1 : 0;
+    const char *rg = getenv("SGL_RING");
+    g.ringSize = rg ? std::min(std::max(atoi(rg), 3), SGL_ARENAS) : 4;
+    const char *rbm = getenv("SGL_RB_MODE");
+    g.rbMode = rbm ? atoi(rbm) : 0;
+    const char *ceu = getenv("SGL_CE_UPLOAD");
+    g.ceUpload = (ceu && atoi(ceu) != 0) ? 1 : 0;
     const char *ns1 = getenv("SGL_NO_SPLIT1");
     g.noSplit1 = (ns1 && atoi(ns1) != 0) ? 1 : 0;
     const char *nl = getenv("SGL_NO_LAZY_VARYINGS");
@@ -542,6 +555,7 @@ int sgl_shutdown(void) {
     if (t.rbDone) cudaEventDestroy(t.rbDone);
   }
   for (void *p : g.rbStage) if (p) cudaFree(p);
+  for (auto &e : g.rbStageFree) { if (e) cudaEventDestroy(e); e = nullptr; }
   if (g.copyStream) cudaStreamDestroy(g.copyStream);
   if (g.copyReady) cudaEventDestroy(g.copyReady);
   if (g.dTextures) cudaFree(g.dTextures);
@@ -952,11 +966,39 @@ int sgl_texture_readback_async(int handle, int layer, int level, int kind, void 
   }
   if (bytes < need) return fail(SGL_ERR_INVALID, "readback buffer too small");
   if (!t->rbDone) CU(cudaEventCreateWithFlags(&t->rbDone, cudaEventDisableTiming));
-  CU(cudaEventRecord(g.copyReady, g.stream));
-  CU(cudaStreamWaitEvent(g.copyStream, g.copyReady, 0));
   cudaPointerAttributes pa;
   const bool toDevice = cudaPointerGetAttributes(&pa, host_out) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
   cudaGetLastError();   // unregistered host memory reports an error on old drivers: not ours to keep
+  if (!toDevice && g.rbMode == 1 && need % 16 == 0) {
+    // to the host, snapshot taken by a copy kernel on the RENDERING stream (a few microseconds at HBM speed, in stream order
+    // behind the pass that produced the image, so no later pass ever waits for anything); only the PCIe copy of the
+    // snapshot runs on the copy stream.  The staging buffer is reused two read-backs later, after its PCIe copy.
+    const int k = g.rbStageNext;
+    g.rbStageNext ^= 1;
+    if (g.rbStageCap[k] < need) {
+      CU(cudaStreamSynchronize(g.copyStream));
+      if (g.rbStage[k]) CU(cudaFree(g.rbStage[k]));
+      g.rbStage[k] = nullptr;
+      g.rbStageCap[k] = 0;
+      cudaError_t e = cudaMalloc(&g.rbStage[k], need);
+      if (e != cudaSuccess) return fail(SGL_ERR_OOM, "read-back staging of %zu bytes: %s", need, cudaGetErrorString(e));
+      g.rbStageCap[k] = need;
+    }
+    if (!g.rbStageFree[k]) CU(cudaEventCreateWithFlags(&g.rbStageFree[k], cudaEventDisableTiming));
+    else CU(cudaStreamWaitEvent(g.stream, g.rbStageFree[k], 0));
+    const size_t n16 = need / 16;
+    int rc = launch("sglCopy16Kernel", sglCopy16Kernel, dim3((unsigned) std::min<size_t>((n16 + 255) / 256, 148 * 8)), dim3(256),
+                    (uint4 *) g.rbStage[k], (const uint4 *) src, n16);
+    if (rc) return rc;
+    CU(cudaEventRecord(g.copyReady, g.stream));
+    CU(cudaStreamWaitEvent(g.copyStream, g.copyReady, 0));
+    CU(cudaMemcpyAsync(host_out, g.rbStage[k], need, cudaMemcpyDeviceToHost, g.copyStream));
+    CU(cudaEventRecord(g.rbStageFree[k], g.copyStream));
+    g.hostD2H += need;
+    return SGL_OK;
+  }
+  CU(cudaEventRecord(g.copyReady, g.stream));
+  CU(cudaStreamWaitEvent(g.copyStream, g.copyReady, 0));
   if (toDevice) {
     // the destination is device memory -- another GPU's frame store mapped with sgl_peer_open (copy-engine form of the
     // multi-GPU gather): one copy
@@ -1216,10 +1258,13 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   size_t oStream = depthOnly ? 0 : take((size_t) 128 * std::max<size_t>(streamCapacity, 1));
   SecTimer sec(6);
   auto section = [&](int k) { sec.switchTo(k); };
-  const int arenaSlot = g.arenaNext % (off <= SGL_SMALL_ARENA_BYTES && !g.fewArenas ? SGL_ARENAS : 3);
+  // the deep ring only for a run of small passes (a view farm); one large pass (config 2's main pass) and the ring is three
+  // deep again -- with eight frames of geometry kernels in flight next to a long pixel stage config 2 lost 5 %
+  g.smallStreak = (off <= SGL_SMALL_ARENA_BYTES && nTiles <= 4096) ? std::min(g.smallStreak + 1, 1 << 20) : 0;
+  const int arenaSlot = g.arenaNext % (g.smallStreak > SGL_ARENAS && !g.fewArenas ? SGL_ARENAS : g.ringSize);
   Ctx::Arena &arena = g.arenas[arenaSlot];
   const cudaStream_t geomStream = g.geomStreams[arenaSlot];
-  g.arenaNext = (g.arenaNext + 1) % (SGL_ARENAS * 3);
+  g.arenaNext = (g.arenaNext + 1) % (SGL_ARENAS * 3 * 5 * 7);   // a multiple of every ring size
   int rc = ensureArena(arena, off);
   if (rc) return rc;
   uint8_t *A = arena.mem;
@@ -1274,10 +1319,16 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   }
   const cudaStream_t geomS = gCur;
   auto issueUpload = [&]() -> int {   // head of the geometry chain: zero the counters, upload the draw records
-    CU(cudaMemsetAsync(A + oZero, 0, zeroBytes, curStream()));
     if (lazyVaryings && usedBytes) CU(cudaMemsetAsync(A + oUsedAll, 0, usedBytes, curStream()));
-    if (nDraws) CU(cudaMemcpyAsync(A + oDraws, arena.stagingHost, recBytes, cudaMemcpyHostToDevice, curStream()));
-    return SGL_OK;
+    if (g.ceUpload) {
+      CU(cudaMemsetAsync(A + oZero, 0, zeroBytes, curStream()));
+      if (nDraws) CU(cudaMemcpyAsync(A + oDraws, arena.stagingHost, recBytes, cudaMemcpyHostToDevice, curStream()));
+      return SGL_OK;
+    }
+    // one kernel: no copy-engine work in the geometry chain (the offsets are 256-byte aligned, the sizes multiples of 16)
+    const size_t n16 = std::max(zeroBytes, recBytes) / 16;
+    return launch("sglPassHeadKernel", sglPassHeadKernel, dim3((unsigned) std::min<size_t>((n16 + 255) / 256, 148 * 4)), dim3(256),
+                  (uint4 *) (A + oZero), zeroBytes / 16, (uint4 *) (A + oDraws), (const uint4 *) arena.stagingHost, recBytes / 16);
   };
 
   section(0);
