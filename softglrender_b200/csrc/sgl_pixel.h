@@ -125,10 +125,10 @@ SGL_HD void sglLineVisit(const SglPrim &p, int px, int py, F &&f) {
   if (k0 < 0) k0 = 0;
   if (k1 > dx) k1 = dx;
   for (int k = k0; k <= k1; k++) {
-    int cx = x0 + k, cy = y0 + sy * sglLineYSteps(k, dx, ady);
     int lo, hi;
-    sglPointSpan((float) cx, width, lo, hi);
-    if (major < lo || major > hi) continue;
+    sglPointSpan((float) (x0 + k), width, lo, hi);       // the cheap axis first: of the 2*reach + 1 candidate steps usually one
+    if (major < lo || major > hi) continue;              // survives, and only that one pays for the division in sglLineYSteps
+    const int cy = y0 + sy * sglLineYSteps(k, dx, ady);
     sglPointSpan((float) cy, width, lo, hi);
     if (minor < lo || minor > hi) continue;
     float t = xdiv((float) k, (float) dx);           // (float)(x - x0) / (float)dx ; 0/0 = NaN for single-column lines

@@ -24,7 +24,8 @@ extern "C" int sglLaunchShade1(const SglPassParams *P, int nTiles, void *stream)
 extern "C" int sglLaunchShade4(const SglPassParams *P, int nTiles, void *stream);
 // depth-only passes (sgl_depth.cu)
 #include "sgl_depth_pass.h"
-extern "C" int sglLaunchDepthOnly(int samples, const SglDepthPass *D, int maxPrims, int nDraws, int nTiles, void *stream);
+extern "C" int sglLaunchDepthSetup(int samples, const SglDepthPass *D, int maxPrims, int nDraws, void *stream);
+extern "C" int sglLaunchDepthRaster(int samples, const SglDepthPass *D, int nTiles, void *stream);
 
 namespace {
 
@@ -1397,28 +1398,6 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
 
   section(2);
   if (depthOnly) {
-    rc = runStage(geomS, hashPod(sig, 0x67656f6dull), [&]() -> int {
-      int r2 = issueUpload();
-      if (r2) return r2;
-      if (maxVerts > 0)      // nothing in a depth-only pass reads varyings
-        return launch("sglVertexKernel<1>", sglVertexKernel<true>, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws);
-      return SGL_OK;
-    });
-    if (rc) return rc;
-    section(3);
-    // pixel stage (the atomic rasteriser writes the depth attachment): on the auxiliary stream when overlap is on
-    const bool aux = overlap;
-    cudaStream_t pix = aux ? g.auxStream : g.stream;
-    if (aux) {
-      CU(cudaEventRecord(g.auxReady, g.stream));           // all earlier pixel work (it may sample this depth texture) first
-      CU(cudaStreamWaitEvent(g.auxStream, g.auxReady, 0));
-      CU(cudaEventRecord(arena.geomDone, geomStream));
-      CU(cudaStreamWaitEvent(g.auxStream, arena.geomDone, 0));
-      gCur = g.auxStream;
-    } else {
-      rc = toPixelStage();
-      if (rc) return rc;
-    }
     SglDepthPass D;
     memset(&D, 0, sizeof(D));
     D.draws = P.draws;
@@ -1437,6 +1416,39 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     D.tileOwner = P.tileOwner;
     D.tilesX = tilesX;
     D.rank = g.rank;
+    // geometry stage: vertex shading (positions only: nothing in a depth-only pass reads varyings) and the primitive-parallel
+    // setup (assembly, clipping, culling, work queues) -- arena only, so it does not wait for earlier pixel work
+    rc = runStage(geomS, hashPod(hashPod(sig, D), 0x67656f6dull), [&]() -> int {
+      int r2 = issueUpload();
+      if (r2) return r2;
+      if (maxVerts > 0) {
+        r2 = launch("sglVertexKernel<1>", sglVertexKernel<true>, dim3((maxVerts + 127) / 128, nDraws), dim3(128), P.draws);
+        if (r2) return r2;
+      }
+      if (maxPrims > 0) {
+        profBegin(samples == 4 ? "sglDepthSetup<4>" : "sglDepthSetup<1>");
+        int e = sglLaunchDepthSetup(samples, &D, maxPrims, nDraws, (void *) curStream());
+        profEnd();
+        g.hostLaunches += 1;
+        if (e != 0) return fail(SGL_ERR_CUDA, "depth-only setup launch failed: %s", cudaGetErrorString((cudaError_t) e));
+      }
+      return SGL_OK;
+    });
+    if (rc) return rc;
+    section(3);
+    // pixel stage (the atomic rasteriser writes the depth attachment): on the auxiliary stream when overlap is on
+    const bool aux = overlap;
+    cudaStream_t pix = aux ? g.auxStream : g.stream;
+    if (aux) {
+      CU(cudaEventRecord(g.auxReady, g.stream));           // all earlier pixel work (it may sample this depth texture) first
+      CU(cudaStreamWaitEvent(g.auxStream, g.auxReady, 0));
+      CU(cudaEventRecord(arena.geomDone, geomStream));
+      CU(cudaStreamWaitEvent(g.auxStream, arena.geomDone, 0));
+      gCur = g.auxStream;
+    } else {
+      rc = toPixelStage();
+      if (rc) return rc;
+    }
     section(5);
     rc = runStage(pix, hashPod(hashPod(sig, D), 0x70697865ull), [&]() -> int {
       if (clearDepthFlag) {
@@ -1448,9 +1460,9 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
       }
       if (maxPrims > 0) {
         profBegin(samples == 4 ? "sglDepthOnly<4>" : "sglDepthOnly<1>");
-        int e = sglLaunchDepthOnly(samples, &D, maxPrims, nDraws, nTiles, (void *) curStream());
+        int e = sglLaunchDepthRaster(samples, &D, nTiles, (void *) curStream());
         profEnd();
-        g.hostLaunches += 3;
+        g.hostLaunches += 2;
         if (e != 0) return fail(SGL_ERR_CUDA, "depth-only kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
       }
       return SGL_OK;

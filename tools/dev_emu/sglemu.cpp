@@ -55,6 +55,7 @@ int sgl_timer_begin(void) { return 0; }
 int sgl_timer_end(float *ms) { *ms = 0; return 0; }
 int sgl_tile_size(void) { return SGL_TILE; }
 int sgl_set_tile_owner_map(const uint8_t *, int, int) { return 0; }
+int sgl_texture_set_shard_halo(int, int) { return 0; }
 
 static const char *kBlocks[8][4] = {{}, {"UniformsModel", "UniformsMaterial"}, {"UniformsModel", "UniformsScene", "UniformsMaterial"},
   {"UniformsModel", "UniformsScene", "UniformsMaterial"}, {"UniformsModel"}, {"UniformsModel"}, {"UniformsModel", "UniformsPrefilter"}, {"UniformsQuadFilter"}};
