@@ -108,6 +108,8 @@ typedef struct SglCounters {
   uint64_t vertices_in;       /* VAO vertices of all submitted draws (64 B each) ... */
   uint64_t indices_in;        /* ... and their indices (4 B each): B_geom of the roofline = 64 * vertices_in + 4 * indices_in */
   uint64_t host_ns_wait_gpu;  /* part of host_ns_pass_end spent BLOCKED on the GPU (arena ring full): not CPU work */
+  uint64_t early_vis;         /* visibility kernels that started while the previous pass's shading kernel was still running */
+  uint64_t renamed_passes;    /* depth-only passes that rendered into the texture's other backing store instead of waiting for its readers */
 } SglCounters;
 
 /* ---- context ---------------------------------------------------------------------------------------- */

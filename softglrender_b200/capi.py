@@ -38,7 +38,7 @@ class SglDraw(C.Structure):
 class SglCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("passes", "draws", "primitives_in", "primitives_binned",
                                           "fragments_shaded", "samples_written", "kernel_launches", "clip_overflow",
-                                          "h2d_bytes", "d2h_bytes", "host_ns_pass_end", "host_ns_draw", "bin_spills", "vertices_in", "indices_in", "host_ns_wait_gpu")]
+                                          "h2d_bytes", "d2h_bytes", "host_ns_pass_end", "host_ns_draw", "bin_spills", "vertices_in", "indices_in", "host_ns_wait_gpu", "early_vis", "renamed_passes")]
 
 
 class SglKernelTime(C.Structure):

@@ -722,6 +722,9 @@ __global__ void sglCopy16Kernel(uint4 *dst, const uint4 *src, size_t n16) {
   for (; i < n16; i += stride) dst[i] = src[i];
 }
 
+// device texture table: a renamed depth texture's entry learns its new backing store (sglcuda.cu, "Renaming")
+__global__ void sglSetTexBaseKernel(SglTexObj *entry, uint8_t *base) { entry->base = base; }
+
 // ---- known-answer-test kernels (wrap the device functions above) ---------------------------------------------
 __global__ void sglKatBarycentricKernel(const float *tri, const float *xy, int n, float *bcOut, int *insideOut, float *zwOut) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -44,6 +44,8 @@ struct TextureRec {
                             // under a tile-owner map (< 0: every tile -- the texture is replicated)
   cudaEvent_t rbDone = nullptr;   // completion of the last sgl_texture_readback_async on the copy stream
   bool rbPending = false;         // a later pass that overwrites the colour image must wait for rbDone on the device
+  void *altBase = nullptr;        // second backing store of a depth texture whose depth-only passes are renamed (see runPass)
+  bool exposed = false;           // sgl_texture_device_ptr handed the storage out: work the library cannot see may touch it in stream order
 };
 
 #define SGL_ARENAS 8
@@ -114,8 +116,24 @@ struct Ctx {
   int noSplit1 = 0;            // SGL_NO_SPLIT1=1: single-sample heavy tiles are not split (A/B runs)
   int noSplit = 0;             // SGL_NO_SPLIT=1: heavy MSAA tiles are not split into quarter-tile CTAs (A/B runs)
   void *dummyTexels = nullptr; // backing store of texture table entry 0
-  uint32_t *vis = nullptr;     // visibility buffer of the deferred path
-  size_t visCap = 0;
+  uint32_t *vis[2] = {nullptr, nullptr};   // visibility buffers of the deferred path (two: see "early visibility" in runPass)
+  size_t visCap[2] = {0, 0};
+  int visNext = 0;
+  // Early visibility: the visibility kernel of pass n+1 may start while the shading kernel of pass n still runs (it reads the
+  // other visibility buffer and touches neither the colour attachment nor anything pass n samples).  It is launched on visStream
+  // behind preShade -- the position of the rendering stream just BEFORE pass n's shading kernel -- which is only legal while
+  // nothing else has been queued on the rendering stream since that kernel: mainSeq counts every such submission.
+  cudaStream_t visStream = nullptr;
+  cudaEvent_t preShade = nullptr, visDone = nullptr;
+  unsigned long long mainSeq = 1, seqAfterShade = 0;
+  std::vector<int> lastShadeSampled;   // textures bound to the draws of the pass whose shading kernel was launched last
+  // Renaming: a depth-only pass that clears a single-level depth texture (the shadow map of every frame) renders into the
+  // texture's OTHER backing store, so it does not have to wait for the shading kernel that still samples the previous
+  // contents; the device texture table learns the new address in stream order before the next kernel that samples.
+  std::vector<int> pendingTexBase;   // handles whose table entry still shows the previous backing store
+  int noRename = 0;            // SGL_NO_RENAME=1 (A/B runs, tests)
+  unsigned long long hostRenames = 0;
+  int noEarlyVis = 0;          // SGL_NO_EARLY_VIS=1: every visibility kernel on the rendering stream (A/B runs, tests)
   int forceFused = 0;          // SGL_FORCE_FUSED=1: always use the fused tile kernel (A/B runs, tests)
   // multi-GPU
   uint8_t *dTileOwner = nullptr;
@@ -134,6 +152,7 @@ struct Ctx {
   unsigned int *dOverflow = nullptr;   // device alias of hOverflow
   int clipScale = 1;                   // grows after an overflow: clip-vertex / fan arenas of later passes are this much larger
   long long binCapLimit = 0, clipMinVerts = 65536, clipMinFans = 32768;   // sgl_debug_set_limits (tests shrink them)
+  unsigned long long hostEarlyVis = 0;   // visibility kernels that started ahead of the previous pass's shading kernel
   unsigned long long hostLaunches = 0, hostPasses = 0, hostDraws = 0, hostH2D = 0, hostD2H = 0, hostNsPassEnd = 0, hostNsDraw = 0, hostVertices = 0, hostIndices = 0, hostNsWaitGpu = 0;
   cudaEvent_t evBegin = nullptr, evEnd = nullptr;
   std::string err;
@@ -168,10 +187,16 @@ void joinAux();
   if (!g.ready) return fail(SGL_ERR_STATE, "sgl_init has not been called (or failed)")
 #define NEED_CTX()        \
   NEED_CTX_RECORDING();   \
+  g.mainSeq++;            \
+  if (!g.pendingTexBase.empty()) { int rcTb = flushTexBases(); if (rcTb) return rcTb; } \
   joinAux()
 
+// queues (on the rendering stream, i.e. behind every kernel that still samples the old contents) the table updates of
+// renamed depth textures; must precede any kernel that samples textures
+int flushTexBases();
 void joinAux() {
   if (!g.auxPending) return;
+  g.mainSeq++;     // later rendering-stream work is ordered behind the auxiliary passes from here on; an early visibility kernel would not be
   cudaStreamWaitEvent(g.stream, g.auxDone, 0);
   g.auxPending = false;
   g.auxDepthTex.clear();
@@ -219,6 +244,7 @@ int syncAll() {
   CU(cudaStreamSynchronize(g.stream));
   for (cudaStream_t gs : g.geomStreams) if (gs) CU(cudaStreamSynchronize(gs));
   if (g.auxStream) CU(cudaStreamSynchronize(g.auxStream));
+  if (g.visStream) CU(cudaStreamSynchronize(g.visStream));
   if (g.peerStream) CU(cudaStreamSynchronize(g.peerStream));
   g.auxPending = false;
   g.auxDepthTex.clear();
@@ -354,8 +380,20 @@ int launch(const char *name, void (*kernel)(Args...), dim3 grid, dim3 block, Arg
   kernel<<<grid, block, 0, curStream()>>>(args...);
   profEnd();
   g.hostLaunches++;
+  if (curStream() == g.stream) g.mainSeq++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(SGL_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e));
+  return SGL_OK;
+}
+
+int flushTexBases() {
+  struct CurGuard { cudaStream_t saved; ~CurGuard() { gCur = saved; } } guard{gCur};
+  gCur = g.stream;
+  for (int h : g.pendingTexBase) {
+    int rc = launch("sglSetTexBaseKernel", sglSetTexBaseKernel, dim3(1), dim3(1), g.dTextures + h, g.textures[h].obj.base);
+    if (rc) return rc;
+  }
+  g.pendingTexBase.clear();
   return SGL_OK;
 }
 
@@ -408,6 +446,7 @@ template<class F>
 int runStage(cudaStream_t s, uint64_t key, F issue) {
   struct CurGuard { cudaStream_t saved; ~CurGuard() { gCur = saved; } } guard{gCur};
   gCur = s;
+  if (s == g.stream) g.mainSeq++;
   if (g.noGraphs || gProfiling) return issue();
   for (auto &e : gStageGraphs)
     if (e.key == key) {
@@ -491,7 +530,10 @@ int sgl_init(int device_ordinal, int rank, int world) {
     CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     for (auto &gs : g.geomStreams) CU(cudaStreamCreateWithPriority(&gs, cudaStreamNonBlocking, hi));
     CU(cudaStreamCreateWithPriority(&g.auxStream, cudaStreamNonBlocking, hi));   // small kernels next to a visibility kernel
+    CU(cudaStreamCreateWithFlags(&g.visStream, cudaStreamNonBlocking));          // early visibility kernels (same priority as the rendering stream)
   }
+  CU(cudaEventCreateWithFlags(&g.preShade, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&g.visDone, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&g.auxReady, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&g.auxDone, cudaEventDisableTiming));
   CU(cudaStreamCreateWithFlags(&g.copyStream, cudaStreamNonBlocking));
@@ -523,6 +565,10 @@ int sgl_init(int device_ordinal, int rank, int world) {
     g.noSplit = (ns && atoi(ns) != 0) ? 1 : 0;
     const char *fa = getenv("SGL_FEW_ARENAS");
     g.fewArenas = (fa && atoi(fa) != 0) ? 1 : 0;
+    const char *nrn = getenv("SGL_NO_RENAME");
+    g.noRename = (nrn && atoi(nrn) != 0) ? 1 : 0;
+    const char *nev = getenv("SGL_NO_EARLY_VIS");
+    g.noEarlyVis = (nev && atoi(nev) != 0) ? 1 : 0;
     const char *rg = getenv("SGL_RING");
     g.ringSize = rg ? std::min(std::max(atoi(rg), 3), SGL_ARENAS) : 4;
     const char *rbm = getenv("SGL_RB_MODE");
@@ -552,6 +598,7 @@ int sgl_shutdown(void) {
   if (g.copyStream) cudaStreamSynchronize(g.copyStream);
   for (auto &t : g.textures) {
     if (t.alive && t.obj.base) cudaFree(t.obj.base);
+    if (t.alive && t.altBase) cudaFree(t.altBase);
     if (t.alive && t.obj.resolve) cudaFree(t.obj.resolve);
     if (t.rbDone) cudaEventDestroy(t.rbDone);
   }
@@ -570,9 +617,12 @@ int sgl_shutdown(void) {
   for (cudaStream_t gs : g.geomStreams) if (gs) cudaStreamDestroy(gs);
   if (g.auxStream) { cudaStreamSynchronize(g.auxStream); cudaStreamDestroy(g.auxStream); }
   if (g.peerStream) { cudaStreamSynchronize(g.peerStream); cudaStreamDestroy(g.peerStream); }
+  if (g.visStream) { cudaStreamSynchronize(g.visStream); cudaStreamDestroy(g.visStream); }
+  if (g.preShade) cudaEventDestroy(g.preShade);
+  if (g.visDone) cudaEventDestroy(g.visDone);
   if (g.auxReady) cudaEventDestroy(g.auxReady);
   if (g.auxDone) cudaEventDestroy(g.auxDone);
-  if (g.vis) cudaFree(g.vis);
+  for (auto &v : g.vis) if (v) cudaFree(v);
   if (g.dummyTexels) cudaFree(g.dummyTexels);
   dropHaloMaps();
   if (g.dTileOwner) cudaFree(g.dTileOwner);
@@ -637,6 +687,8 @@ int sgl_get_counters(SglCounters *out) {
   out->vertices_in = g.hostVertices;
   out->host_ns_wait_gpu = g.hostNsWaitGpu;
   out->indices_in = g.hostIndices;
+  out->early_vis = g.hostEarlyVis;
+  out->renamed_passes = g.hostRenames;
   return checkOverflow();
 }
 
@@ -645,6 +697,7 @@ int sgl_reset_counters(void) {
   { int rc = syncAll(); if (rc) return rc; }
   CU(cudaMemset(g.dCounters, 0, 40 * sizeof(unsigned long long)));
   for (auto &v : gHostSec) v = 0;
+  g.hostEarlyVis = g.hostRenames = 0;
   g.hostLaunches = g.hostPasses = g.hostDraws = g.hostH2D = g.hostD2H = g.hostNsPassEnd = g.hostNsDraw = g.hostVertices = g.hostIndices = g.hostNsWaitGpu = 0;
   return SGL_OK;
 }
@@ -836,6 +889,8 @@ int sgl_texture_destroy(int handle) {
   CU(cudaStreamSynchronize(g.stream));
   CU(cudaStreamSynchronize(g.copyStream));
   if (t->obj.base) CU(cudaFree(t->obj.base));
+  if (t->altBase) CU(cudaFree(t->altBase));
+  t->altBase = nullptr;
   if (t->obj.resolve) CU(cudaFree(t->obj.resolve));
 #ifdef SGL_TOUCH_BITMAP
   if (t->obj.touch) CU(cudaFree(t->obj.touch));
@@ -901,6 +956,7 @@ int sgl_texture_device_ptr(int handle, int layer, int level, int kind, void **pt
   TextureRec *t = tex(handle);
   if (!t || layer < 0 || layer >= t->obj.layers || level < 0 || level >= t->obj.levels) return fail(SGL_ERR_INVALID, "bad texture/layer/level");
   int w = sglLevelDim(t->obj.width, level), h = sglLevelDim(t->obj.height, level);
+  t->exposed = true;
   if (kind == 1) {
     if (!t->obj.resolve) return fail(SGL_ERR_INVALID, "texture has no resolved colour buffer");
     *ptr_out = t->obj.resolve;
@@ -950,6 +1006,10 @@ int sgl_texture_readback(int handle, int layer, int level, int kind, void *host_
 // next frame's vertex / setup / binning / visibility kernels execute; a later pass that overwrites the image waits for
 // the copy on the device (sgl_pass_end), so the caller never has to fence.  The host buffer should be pinned.
 int sgl_texture_readback_async(int handle, int layer, int level, int kind, void *host_out, size_t bytes) {
+  // a copy-stream read of an RGBA8 image puts no work on the rendering stream and no visibility kernel touches colour: the
+  // next pass may still start its visibility kernel early (mainSeq restored below)
+  const unsigned long long seqAtEntry = g.mainSeq;
+  const bool auxWasPending = g.auxPending;
   NEED_CTX();
   TextureRec *t = tex(handle);
   if (!t || layer < 0 || layer >= t->obj.layers || level < 0 || level >= t->obj.levels) return fail(SGL_ERR_INVALID, "bad texture/layer/level");
@@ -1026,6 +1086,7 @@ int sgl_texture_readback_async(int handle, int layer, int level, int kind, void 
     g.hostD2H += need;
   }
   t->rbPending = true;
+  if (!auxWasPending) g.mainSeq = seqAtEntry;
   return SGL_OK;
 }
 
@@ -1177,6 +1238,28 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   // lazy varyings: in a sharded pass most primitives reach none of this rank's tiles, so the vertex kernel computes
   // positions only and sglVaryingKernel runs the full vertex shader for the vertices of the primitives that were emitted
   const bool lazyVaryings = tileOwner != nullptr && !depthOnly && !g.noLazyVaryings;
+  // renaming (see Ctx): only in the plain steady-state pattern -- nothing but event traffic on the rendering stream since the
+  // last shading kernel, no other auxiliary pass in flight, whole single-level texture cleared and rendered by this rank
+  // Only in a run of small passes (small frames, view farms: smallStreak), where the chain shading -> next shadow pass ->
+  // next shading is what limits throughput (config 5 +13 %, config 1 +11 %); next to a large main pass the shadow pass hides
+  // behind the visibility kernel anyway and an earlier start only takes SMs from the shading kernel (config 2 -3 %).
+  bool renamed = false;
+  if (depthOnly && clearDepthFlag && !g.noRename && g.smallStreak >= 2 && !g.noOverlap && !gProfiling && !tileOwner && !g.auxPending && g.preShade &&
+      g.seqAfterShade == g.mainSeq && !dt->exposed && dt->obj.levels == 1 && dt->obj.layers == 1 && dt->obj.samples == 1 && !dt->rbPending &&
+      std::find(g.pendingTexBase.begin(), g.pendingTexBase.end(), g.depthTex) == g.pendingTexBase.end()) {
+    if (!dt->altBase) {
+      cudaError_t e = cudaMalloc(&dt->altBase, dt->bytes);     // once per texture
+      if (e != cudaSuccess) { cudaGetLastError(); dt->altBase = nullptr; }
+    }
+    if (dt->altBase) {
+      void *cur = dt->obj.base;
+      dt->obj.base = (uint8_t *) dt->altBase;
+      dt->altBase = cur;
+      g.pendingTexBase.push_back(g.depthTex);
+      g.hostRenames++;
+      renamed = true;
+    }
+  }
   // ---- arena layout
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = alignUp(off + bytes, 256); return o; };
@@ -1440,8 +1523,13 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     const bool aux = overlap;
     cudaStream_t pix = aux ? g.auxStream : g.stream;
     if (aux) {
-      CU(cudaEventRecord(g.auxReady, g.stream));           // all earlier pixel work (it may sample this depth texture) first
-      CU(cudaStreamWaitEvent(g.auxStream, g.auxReady, 0));
+      if (renamed) {
+        // the other backing store was last sampled by the shading kernel BEFORE the one that may still be running
+        CU(cudaStreamWaitEvent(g.auxStream, g.preShade, 0));
+      } else {
+        CU(cudaEventRecord(g.auxReady, g.stream));           // all earlier pixel work (it may sample this depth texture) first
+        CU(cudaStreamWaitEvent(g.auxStream, g.auxReady, 0));
+      }
       CU(cudaEventRecord(arena.geomDone, geomStream));
       CU(cudaStreamWaitEvent(g.auxStream, arena.geomDone, 0));
       gCur = g.auxStream;
@@ -1528,8 +1616,8 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   section(3);
   rc = toPixelStage();
   if (rc) return rc;
-  if (g.auxPending && (!overlap || std::find(g.auxDepthTex.begin(), g.auxDepthTex.end(), g.depthTex) != g.auxDepthTex.end()))
-    joinAux();   // this pass writes a depth texture an auxiliary-stream pass is still producing
+  const bool needAuxJoin = g.auxPending && (!overlap || std::find(g.auxDepthTex.begin(), g.auxDepthTex.end(), g.depthTex) != g.auxDepthTex.end());
+  if (needAuxJoin) joinAux();   // this pass writes a depth texture an auxiliary-stream pass is still producing
   // Deferred (visibility + shading) path for passes made of opaque draws whose point/line programs have no varyings;
   // everything else (blending, wireframe with a lit program) takes the fused tile kernel.
   bool deferred = !g.forceFused;
@@ -1541,37 +1629,68 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   }
   section(4);
   if (deferred) {
+    const int vk = ct ? (g.visNext ^= 1) : 0;
     if (ct) {
       size_t need = (size_t) fbW * fbH * samples * sizeof(uint32_t);
-      if (need > g.visCap) {
+      if (need > g.visCap[vk]) {
         CU(cudaStreamSynchronize(g.stream));
-        if (g.vis) CU(cudaFree(g.vis));
-        g.vis = nullptr;
-        g.visCap = 0;
-        cudaError_t e = cudaMalloc(&g.vis, need);
+        if (g.visStream) CU(cudaStreamSynchronize(g.visStream));
+        if (g.vis[vk]) CU(cudaFree(g.vis[vk]));
+        g.vis[vk] = nullptr;
+        g.visCap[vk] = 0;
+        cudaError_t e = cudaMalloc(&g.vis[vk], need);
         if (e != cudaSuccess) return fail(SGL_ERR_OOM, "visibility buffer of %zu bytes: %s", need, cudaGetErrorString(e));
-        g.visCap = need;
+        g.visCap[vk] = need;
       }
-      P.vis = g.vis;
+      P.vis = g.vis[vk];
+    }
+    // early visibility (see Ctx): nothing but event traffic has reached the rendering stream since the last shading kernel,
+    // that kernel reads the other visibility buffer, its pass does not sample this pass's depth texture, and no auxiliary
+    // pass or outside party touches that texture
+    bool early = overlap && ct && !g.noEarlyVis && !needAuxJoin && g.visStream && g.seqAfterShade == g.mainSeq && !P.tileTimes;
+    if (early && dt) {
+      if (dt->exposed || std::find(g.lastShadeSampled.begin(), g.lastShadeSampled.end(), g.depthTex) != g.lastShadeSampled.end()) early = false;
+    }
+    cudaStream_t visS = early ? g.visStream : g.stream;
+    if (early) {
+      CU(cudaStreamWaitEvent(g.visStream, arena.geomDone, 0));
+      CU(cudaStreamWaitEvent(g.visStream, g.preShade, 0));
+      gCur = g.visStream;
     }
     profBegin(samples == 4 ? "sglVisKernel<4>" : "sglVisKernel<1>");
-    int e = sglLaunchVis(samples, &P, nTiles, (void *) g.stream);
+    int e = sglLaunchVis(samples, &P, nTiles, (void *) visS);
     profEnd();
     g.hostLaunches++;
     if (e != 0) return fail(SGL_ERR_CUDA, "visibility kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
+    if (early) {
+      CU(cudaEventRecord(g.visDone, g.visStream));
+      CU(cudaStreamWaitEvent(g.stream, g.visDone, 0));
+      gCur = g.stream;
+      g.hostEarlyVis++;
+    }
+    g.mainSeq++;
+    if (!g.pendingTexBase.empty()) { int rcTb = flushTexBases(); if (rcTb) return rcTb; }
     joinAux();   // the shading kernel samples textures (shadow maps): depth-only passes on the auxiliary stream first
     if (ct) {
       if (ct->rbPending) {   // an asynchronous read-back of this image is still in flight: overwrite only after it
         CU(cudaStreamWaitEvent(g.stream, ct->rbDone, 0));
         ct->rbPending = false;
       }
+      if (g.preShade) CU(cudaEventRecord(g.preShade, g.stream));
       profBegin(samples == 4 ? "sglShadeKernel<4>" : "sglShadeKernel<1>");
       e = samples == 4 ? sglLaunchShade4(&P, nTiles, (void *) g.stream) : sglLaunchShade1(&P, nTiles, (void *) g.stream);
       profEnd();
       g.hostLaunches++;
       if (e != 0) return fail(SGL_ERR_CUDA, "shading kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
+      g.seqAfterShade = ++g.mainSeq;
+      g.lastShadeSampled.clear();
+      for (int i = 0; i < nDraws; i++)
+        for (const SglSamplerSlot &sl : draws[i].samplers)
+          if (sl.tex > 0 && std::find(g.lastShadeSampled.begin(), g.lastShadeSampled.end(), sl.tex) == g.lastShadeSampled.end())
+            g.lastShadeSampled.push_back(sl.tex);
     }
   } else {
+    if (!g.pendingTexBase.empty()) { int rcTb = flushTexBases(); if (rcTb) return rcTb; }
     joinAux();
     if (ct && ct->rbPending) {
       CU(cudaStreamWaitEvent(g.stream, ct->rbDone, 0));
@@ -1581,6 +1700,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
     int e = samples == 4 ? sglLaunchRaster4(&P, nTiles, (void *) g.stream) : sglLaunchRaster1(&P, nTiles, (void *) g.stream);
     profEnd();
     g.hostLaunches++;
+    g.mainSeq++;
     if (e != 0) return fail(SGL_ERR_CUDA, "raster kernel launch failed: %s", cudaGetErrorString((cudaError_t) e));
   }
   return passDone();
