@@ -431,8 +431,9 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS) sglRasterKernel(SglPassParam
     }
     if (hasColor && !P.clearColorFlag) {
       if (NS == 4) {
-        uint4 cq = reinterpret_cast<const uint4 *>(P.colorBase)[pix];
-        st.color[0] = cq.x; st.color[NS > 1 ? 1 : 0] = cq.y; st.color[NS > 2 ? 2 : 0] = cq.z; st.color[NS > 3 ? 3 : 0] = cq.w;
+        uint32_t c4[4];
+        sglLoadMsColor(P, pix, c4);
+        st.color[0] = c4[0]; st.color[NS > 1 ? 1 : 0] = c4[1]; st.color[NS > 2 ? 2 : 0] = c4[2]; st.color[NS > 3 ? 3 : 0] = c4[3];
       } else st.color[0] = reinterpret_cast<const uint32_t *>(P.colorBase)[pix];
     }
   };
@@ -537,8 +538,10 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS) sglRasterKernel(SglPassParam
     }
     if (hasColor) {
       if (NS == 4) {
-        reinterpret_cast<uint4 *>(P.colorBase)[pix] =
-            make_uint4(st.color[0], st.color[NS > 1 ? 1 : 0], st.color[NS > 2 ? 2 : 0], st.color[NS > 3 ? 3 : 0]);
+        {
+          const uint32_t c4[4] = {st.color[0], st.color[NS > 1 ? 1 : 0], st.color[NS > 2 ? 2 : 0], st.color[NS > 3 ? 3 : 0]};
+          sglStoreMsColor(P, pix, c4);
+        }
         if (P.resolveBase) {
           uint32_t r = 0;
 #pragma unroll
@@ -724,6 +727,19 @@ __global__ void sglCopy16Kernel(uint4 *dst, const uint4 *src, size_t n16) {
 
 // device texture table: a renamed depth texture's entry learns its new backing store (sglcuda.cu, "Renaming")
 __global__ void sglSetTexBaseKernel(SglTexObj *entry, uint8_t *base) { entry->base = base; }
+
+// per-sample records of the pixels whose mask says "samples equal" (sgl_pixel.h, multisample colour storage), before the
+// per-sample image leaves the library (read-back, sgl_texture_device_ptr)
+__global__ void sglMsExpandKernel(uint4 *color, const uint32_t *resolve, uint8_t *mask, size_t n) {
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (; i < n; i += stride)
+    if (mask[i] == 0) {
+      const uint32_t r = resolve[i];
+      color[i] = make_uint4(r, r, r, r);
+      mask[i] = 1;
+    }
+}
 
 // ---- known-answer-test kernels (wrap the device functions above) ---------------------------------------------
 __global__ void sglKatBarycentricKernel(const float *tri, const float *xy, int n, float *bcOut, int *insideOut, float *zwOut) {

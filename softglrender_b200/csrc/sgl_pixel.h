@@ -195,3 +195,31 @@ SGL_HD void sglPixelPrim(const SglPassParams &P, const SglPrim &p, uint32_t slot
     sglWriteImmediate<NS>(P, p, sglRunFragmentShader(&d, P.textures, vary), mask, px, py, st);
   });
 }
+
+// ---- multisample colour storage ---------------------------------------------------------------------------------
+// A pixel whose four samples hold the same colour (everything but primitive edges) keeps only its resolved colour -- which
+// then equals each sample exactly, sum / 4 of four equal bytes -- and a 0 in the per-pixel mask; the 16-byte per-sample
+// record is written for the other pixels only.  In a frame that starts with a clear and ends in the resolve nobody reads the
+// per-sample image, and it was 33 MB of the shading kernel's 84 MB of DRAM traffic on config 2.  Readers (a pass that loads
+// the attachment, the fused tail of a split pass) go through sglLoadMsColor; the per-sample read-back expands first
+// (sglMsExpandKernel).  P.colorMask == null: every record is written, as before.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void sglLoadMsColor(const SglPassParams &P, size_t pix, uint32_t *color) {
+  if (P.colorMask && P.colorMask[pix] == 0) {
+    const uint32_t r = reinterpret_cast<const uint32_t *>(P.resolveBase)[pix];
+    color[0] = color[1] = color[2] = color[3] = r;
+    return;
+  }
+  const uint4 cq = reinterpret_cast<const uint4 *>(P.colorBase)[pix];
+  color[0] = cq.x; color[1] = cq.y; color[2] = cq.z; color[3] = cq.w;
+}
+// per-sample record (when needed) + mask; the caller writes the resolved colour
+__device__ __forceinline__ void sglStoreMsColor(const SglPassParams &P, size_t pix, const uint32_t *color) {
+  if (P.colorMask) {
+    const bool same = color[0] == color[1] && color[1] == color[2] && color[2] == color[3];
+    P.colorMask[pix] = same ? 0 : 1;
+    if (same) return;
+  }
+  reinterpret_cast<uint4 *>(P.colorBase)[pix] = make_uint4(color[0], color[1], color[2], color[3]);
+}
+#endif

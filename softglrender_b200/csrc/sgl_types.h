@@ -115,6 +115,8 @@ struct SglPassParams {
   uint8_t *colorBase;       // RGBA8 [y][x][sample] of the attached layer/level, or null
   float *depthBase;         // float [y][x][sample], or null
   uint8_t *resolveBase;     // resolved colour (MS only), or null
+  uint8_t *colorMask;       // MS only, or null: one byte per pixel, 0 = the four samples are equal and only the resolved colour
+                            // (== each sample) is stored, 1 = the 16-byte per-sample record in colorBase is valid (sglStoreMsColor)
   uint8_t *mirrorBase;      // optional second destination of the final colour (resolved colour for MS targets), linear
                             // RGBA8 [y][x]; may be peer memory of another GPU (multi-GPU gather by direct store), or null
   uint32_t *vis;            // visibility buffer of the deferred path: owner (slot | shading sample << 29) [y][x][sample]

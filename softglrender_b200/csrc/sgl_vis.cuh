@@ -735,8 +735,9 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS, SGL_SHADE_MIN_BLOCKS) sglSha
       uint4 o = reinterpret_cast<const uint4 *>(P.vis)[pix];
       owner[0] = o.x; owner[NS > 1 ? 1 : 0] = o.y; owner[NS > 2 ? 2 : 0] = o.z; owner[NS > 3 ? 3 : 0] = o.w;
       if (!P.clearColorFlag) {
-        uint4 cq = reinterpret_cast<const uint4 *>(P.colorBase)[pix];
-        color[0] = cq.x; color[NS > 1 ? 1 : 0] = cq.y; color[NS > 2 ? 2 : 0] = cq.z; color[NS > 3 ? 3 : 0] = cq.w;
+        uint32_t c4[4];
+        sglLoadMsColor(P, pix, c4);
+        color[0] = c4[0]; color[NS > 1 ? 1 : 0] = c4[1]; color[NS > 2 ? 2 : 0] = c4[2]; color[NS > 3 ? 3 : 0] = c4[3];
       }
     } else {
       owner[0] = P.vis[pix];
@@ -768,7 +769,10 @@ __global__ void __launch_bounds__(SGL_TILE_THREADS, SGL_SHADE_MIN_BLOCKS) sglSha
 
   if (inFb) {
     if (NS == 4) {
-      reinterpret_cast<uint4 *>(P.colorBase)[pix] = make_uint4(color[0], color[NS > 1 ? 1 : 0], color[NS > 2 ? 2 : 0], color[NS > 3 ? 3 : 0]);
+      {
+        const uint32_t c4[4] = {color[0], color[NS > 1 ? 1 : 0], color[NS > 2 ? 2 : 0], color[NS > 3 ? 3 : 0]};
+        sglStoreMsColor(P, pix, c4);
+      }
       if (P.resolveBase) {   // multiSampleResolve (RendererSoft.cpp:880-912): u8vec4(sum / 4.f) == exact integer division
         uint32_t r = 0;
 #pragma unroll

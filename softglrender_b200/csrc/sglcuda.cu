@@ -44,6 +44,8 @@ struct TextureRec {
                             // under a tile-owner map (< 0: every tile -- the texture is replicated)
   cudaEvent_t rbDone = nullptr;   // completion of the last sgl_texture_readback_async on the copy stream
   bool rbPending = false;         // a later pass that overwrites the colour image must wait for rbDone on the device
+  uint8_t *cmask = nullptr;       // multisample colour textures: per-pixel "per-sample record valid" mask (sgl_pixel.h)
+  bool cmaskOff = false;          // the per-sample image was handed out (sgl_texture_device_ptr): every record is written from now on
   void *altBase = nullptr;        // second backing store of a depth texture whose depth-only passes are renamed (see runPass)
   bool exposed = false;           // sgl_texture_device_ptr handed the storage out: work the library cannot see may touch it in stream order
 };
@@ -131,6 +133,7 @@ struct Ctx {
   // texture's OTHER backing store, so it does not have to wait for the shading kernel that still samples the previous
   // contents; the device texture table learns the new address in stream order before the next kernel that samples.
   std::vector<int> pendingTexBase;   // handles whose table entry still shows the previous backing store
+  int noMsMask = 0;            // SGL_NO_MS_MASK=1: multisample colour always stored per sample (A/B runs, tests)
   int noRename = 0;            // SGL_NO_RENAME=1 (A/B runs, tests)
   unsigned long long hostRenames = 0;
   int noEarlyVis = 0;          // SGL_NO_EARLY_VIS=1: every visibility kernel on the rendering stream (A/B runs, tests)
@@ -201,6 +204,18 @@ void joinAux() {
   g.auxPending = false;
   g.auxDepthTex.clear();
 }
+
+// API calls whose rendering-stream work (if any) touches nothing a visibility kernel reads or writes -- gather flags,
+// mirror pointers -- do not end the "nothing since the last shading kernel" state that early visibility and renaming need:
+// they restore mainSeq on success (unless they had to join the auxiliary stream).
+struct SeqKeeper {
+  unsigned long long seq = g.mainSeq;
+  bool auxWasPending = g.auxPending;
+  int done(int rc) const {
+    if (rc == SGL_OK && !auxWasPending) g.mainSeq = seq;
+    return rc;
+  }
+};
 
 size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -386,6 +401,16 @@ int launch(const char *name, void (*kernel)(Args...), dim3 grid, dim3 block, Arg
   return SGL_OK;
 }
 
+// the per-sample image of a multisample colour texture is about to be read by something other than the pixel kernels
+int expandMsColor(TextureRec *t) {
+  if (!t->cmask || t->obj.samples == 1) return SGL_OK;
+  struct CurGuard { cudaStream_t saved; ~CurGuard() { gCur = saved; } } guard{gCur};
+  gCur = g.stream;
+  const size_t n = (size_t) t->obj.width * t->obj.height;
+  return launch("sglMsExpandKernel", sglMsExpandKernel, dim3((unsigned) std::min<size_t>((n + 255) / 256, 148 * 8)), dim3(256),
+                (uint4 *) t->obj.base, (const uint32_t *) t->obj.resolve, t->cmask, n);
+}
+
 int flushTexBases() {
   struct CurGuard { cudaStream_t saved; ~CurGuard() { gCur = saved; } } guard{gCur};
   gCur = g.stream;
@@ -565,6 +590,8 @@ int sgl_init(int device_ordinal, int rank, int world) {
     g.noSplit = (ns && atoi(ns) != 0) ? 1 : 0;
     const char *fa = getenv("SGL_FEW_ARENAS");
     g.fewArenas = (fa && atoi(fa) != 0) ? 1 : 0;
+    const char *nmm = getenv("SGL_NO_MS_MASK");
+    g.noMsMask = (nmm && atoi(nmm) != 0) ? 1 : 0;
     const char *nrn = getenv("SGL_NO_RENAME");
     g.noRename = (nrn && atoi(nrn) != 0) ? 1 : 0;
     const char *nev = getenv("SGL_NO_EARLY_VIS");
@@ -599,6 +626,7 @@ int sgl_shutdown(void) {
   for (auto &t : g.textures) {
     if (t.alive && t.obj.base) cudaFree(t.obj.base);
     if (t.alive && t.altBase) cudaFree(t.altBase);
+    if (t.alive && t.cmask) cudaFree(t.cmask);
     if (t.alive && t.obj.resolve) cudaFree(t.obj.resolve);
     if (t.rbDone) cudaEventDestroy(t.rbDone);
   }
@@ -844,6 +872,10 @@ int sgl_texture_create(const SglTextureDesc *desc, int *handle_out) {
   if (desc->multi_sample && desc->format == SGL_FMT_RGBA8) {
     CU(cudaMalloc(&o.resolve, (size_t) o.width * o.height * 4));
     CU(cudaMemsetAsync(o.resolve, 0, (size_t) o.width * o.height * 4, g.stream));
+    if (o.levels == 1 && o.layers == 1 && !g.noMsMask) {   // 0 everywhere = "samples equal the resolved colour" = the zeroed image
+      CU(cudaMalloc(&t.cmask, (size_t) o.width * o.height));
+      CU(cudaMemsetAsync(t.cmask, 0, (size_t) o.width * o.height, g.stream));
+    }
   }
 #ifdef SGL_TOUCH_BITMAP
   {
@@ -891,6 +923,8 @@ int sgl_texture_destroy(int handle) {
   if (t->obj.base) CU(cudaFree(t->obj.base));
   if (t->altBase) CU(cudaFree(t->altBase));
   t->altBase = nullptr;
+  if (t->cmask) CU(cudaFree(t->cmask));
+  t->cmask = nullptr;
   if (t->obj.resolve) CU(cudaFree(t->obj.resolve));
 #ifdef SGL_TOUCH_BITMAP
   if (t->obj.touch) CU(cudaFree(t->obj.touch));
@@ -962,6 +996,11 @@ int sgl_texture_device_ptr(int handle, int layer, int level, int kind, void **pt
     *ptr_out = t->obj.resolve;
     *bytes_out = (size_t) w * h * 4;
   } else {
+    if (t->cmask) {
+      int rc = expandMsColor(t);
+      if (rc) return rc;
+      t->cmaskOff = true;
+    }
     *ptr_out = levelPtr(*t, layer, level);
     *bytes_out = sglLevelTexels(t->obj.layout, w, h) * 4 * t->obj.samples;
   }
@@ -973,6 +1012,7 @@ int sgl_texture_readback(int handle, int layer, int level, int kind, void *host_
   TextureRec *t = tex(handle);
   if (!t || layer < 0 || layer >= t->obj.layers || level < 0 || level >= t->obj.levels) return fail(SGL_ERR_INVALID, "bad texture/layer/level");
   int w = sglLevelDim(t->obj.width, level), h = sglLevelDim(t->obj.height, level);
+  if (kind != 1 && t->cmask) { int rc = expandMsColor(t); if (rc) return rc; }
   CU(cudaStreamSynchronize(g.stream));
   { int rc = checkOverflow(); if (rc) return rc; }
   if (kind == 1) {
@@ -1026,6 +1066,8 @@ int sgl_texture_readback_async(int handle, int layer, int level, int kind, void 
     need = (size_t) w * h * 4 * t->obj.samples;
   }
   if (bytes < need) return fail(SGL_ERR_INVALID, "readback buffer too small");
+  bool expanded = false;
+  if (kind != 1 && t->cmask) { int rc = expandMsColor(t); if (rc) return rc; expanded = true; }
   if (!t->rbDone) CU(cudaEventCreateWithFlags(&t->rbDone, cudaEventDisableTiming));
   cudaPointerAttributes pa;
   const bool toDevice = cudaPointerGetAttributes(&pa, host_out) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
@@ -1086,7 +1128,7 @@ int sgl_texture_readback_async(int handle, int layer, int level, int kind, void 
     g.hostD2H += need;
   }
   t->rbPending = true;
-  if (!auxWasPending) g.mainSeq = seqAtEntry;
+  if (!auxWasPending && !expanded) g.mainSeq = seqAtEntry;
   return SGL_OK;
 }
 
@@ -1421,6 +1463,7 @@ int runPass(std::vector<SglDrawRec> &draws, int clearColorFlag, int clearDepthFl
   P.colorBase = ct ? levelPtr(*ct, g.colorLayer, g.colorLevel) : nullptr;
   P.depthBase = dt ? (float *) levelPtr(*dt, 0, 0) : nullptr;
   P.resolveBase = (ct && samples > 1) ? ct->obj.resolve : nullptr;
+  P.colorMask = (ct && samples > 1 && P.resolveBase && ct->cmask && !ct->cmaskOff && g.colorLayer == 0 && g.colorLevel == 0) ? ct->cmask : nullptr;
   P.mirrorBase = (ct && g.colorLayer == 0 && g.colorLevel == 0) ? (uint8_t *) ct->mirror : nullptr;
   P.fbW = fbW; P.fbH = fbH; P.samples = samples;
   P.clearColorFlag = clearColorFlag;
@@ -1827,13 +1870,14 @@ int sgl_texture_set_shard_halo(int handle, int pixels) {
 }
 
 int sgl_texture_set_mirror(int handle, void *device_ptr) {
+  SeqKeeper keep;
   NEED_CTX();
   TextureRec *t = tex(handle);
   if (!t) return fail(SGL_ERR_INVALID, "bad texture handle %d", handle);
   if (t->obj.format != SGL_FMT_RGBA8 || t->obj.layout != SGL_LAYOUT_LINEAR || t->obj.layers != 1)
     return fail(SGL_ERR_INVALID, "mirror target needs a linear 2D RGBA8 texture");
   t->mirror = device_ptr;
-  return SGL_OK;
+  return keep.done(SGL_OK);
 }
 
 namespace {
@@ -1948,19 +1992,22 @@ int sgl_peer_close(void *ptr) {
 }
 
 int sgl_peer_signal(void *flag_device_ptr, uint32_t value) {
+  SeqKeeper keep;
   NEED_CTX();
-  return launch("sglPeerSignalKernel", sglPeerSignalKernel, dim3(1), dim3(1), (uint32_t *) flag_device_ptr, value);
+  return keep.done(launch("sglPeerSignalKernel", sglPeerSignalKernel, dim3(1), dim3(1), (uint32_t *) flag_device_ptr, value));
 }
 
 int sgl_peer_signal_after_copies(void *flag_device_ptr, uint32_t value) {
+  SeqKeeper keep;
   NEED_CTX();
   gCur = g.copyStream;   // ordered behind every sgl_texture_readback_async queued so far
   int rc = launch("sglPeerSignalKernel", sglPeerSignalKernel, dim3(1), dim3(1), (uint32_t *) flag_device_ptr, value);
   gCur = nullptr;
-  return rc;
+  return keep.done(rc);
 }
 
 int sgl_peer_collect(const void *done_flags, int count, uint32_t value, void *const *consumed_flags, int timeout_ms, int side_stream) {
+  SeqKeeper keep;
   NEED_CTX();
   if (count < 1 || count > 64) return fail(SGL_ERR_INVALID, "peer collect over %d ranks", count);
   SglPeerPtrs pp;
@@ -1970,15 +2017,16 @@ int sgl_peer_collect(const void *done_flags, int count, uint32_t value, void *co
   gCur = side_stream ? g.peerStream : g.stream;
   int rc = launch("sglPeerCollectKernel", sglPeerCollectKernel, dim3(1), dim3(64), (const uint32_t *) done_flags, count, value, pp, cycles, g.dCounters);
   gCur = nullptr;
-  return rc;
+  return keep.done(rc);
 }
 
 int sgl_peer_wait(const void *flags_device_ptr, int count, uint32_t value, int timeout_ms) {
+  SeqKeeper keep;
   NEED_CTX();
   if (count < 1 || count > 1024) return fail(SGL_ERR_INVALID, "peer wait on %d flags", count);
   long long cycles = (long long) std::max(timeout_ms, 1) * 2000000LL;   // ~2 GHz SM clock
-  return launch("sglPeerWaitKernel", sglPeerWaitKernel, dim3(1), dim3((unsigned) ((count + 31) / 32 * 32)), (const uint32_t *) flags_device_ptr, count, value,
-                cycles, g.dCounters);
+  return keep.done(launch("sglPeerWaitKernel", sglPeerWaitKernel, dim3(1), dim3((unsigned) ((count + 31) / 32 * 32)), (const uint32_t *) flags_device_ptr, count, value,
+                          cycles, g.dCounters));
 }
 
 int sgl_peer_timeouts(uint64_t *count_out) {

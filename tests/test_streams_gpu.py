@@ -22,7 +22,7 @@ def _outputs(trace, data, out, env):
 
 
 @pytest.mark.parametrize("env", [{"SGL_NO_OVERLAP": "1"}, {"SGL_NO_SPLIT": "1"}, {"SGL_NO_PASS_SPLIT": "1"}, {"SGL_FORCE_FUSED": "1"}, {"SGL_NO_GRAPHS": "1"},
-                                 {"SGL_NO_EARLY_VIS": "1"}, {"SGL_NO_RENAME": "1"}, {"SGL_RING": "3"}, {"SGL_CE_UPLOAD": "1"}])
+                                 {"SGL_NO_EARLY_VIS": "1"}, {"SGL_NO_RENAME": "1"}, {"SGL_RING": "3"}, {"SGL_CE_UPLOAD": "1"}, {"SGL_NO_MS_MASK": "1"}])
 def test_scheduling_switches_do_not_change_the_frame(env, work_dir):
     """Config 2 at 960x540 MSAA4x (shadow pass on the auxiliary stream, heavy tiles split) and a blended KAT trace
     (pass split into deferred head + fused tail) against the same traces with one mechanism switched off."""
