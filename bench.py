@@ -442,6 +442,8 @@ def main():
             # blocked because the GPU is the bottleneck (the burst figure above includes that)
             "host_cpu_ms_per_step": (ctr["host_ns_pass_end"] + ctr["host_ns_draw"] - ctr["host_ns_wait_gpu"]) / 1e6 / K,
             "host_blocked_on_gpu_ms_per_step": ctr["host_ns_wait_gpu"] / 1e6 / K,
+            # scheduling evidence (rank 0): visibility kernels that started while the previous frame was still being shaded
+            "early_vis_per_step": ctr["early_vis"] / float(K), "early_vis_per_step_e2e": ctr2["early_vis"] / float(K),
             # the e2e region seen from the device (events on the rendering stream) and from the submitting thread: tells a
             # GPU-side slowdown by the copies from a host-side one
             "e2e_device_ms_per_step": e2e_dev_ms.value / K, "e2e_host_blocked_ms_per_step": ctr2["host_ns_wait_gpu"] / 1e6 / K,

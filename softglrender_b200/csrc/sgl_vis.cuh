@@ -18,8 +18,12 @@
 #ifndef SGL_SHADE_MIN_BLOCKS
 #define SGL_SHADE_MIN_BLOCKS 4
 #endif
+// five CTAs per SM (48 registers, 64 B of spills) beat four (64 registers): the kernel waits on fixed-latency dependencies
+// of the exact barycentric sequence, and the fifth CTA's warps fill them -- A/B on B200: config 2 vis 108 -> 103 us,
+// config 3 338 -> 312 us, 2 M-triangle soup 3.71 -> 3.55 ms; six CTAs (40 registers) spill too much (105 us).  The shading
+// kernel is the other way round: 5 / 6 CTAs per SM cost 160 / 166 us against 150 (its callee already spills at 64).
 #ifndef SGL_VIS_MIN_BLOCKS
-#define SGL_VIS_MIN_BLOCKS 4
+#define SGL_VIS_MIN_BLOCKS 5
 #endif
 
 // conservative "can primitive p write into tile (tx,ty)?" beyond the bbox overlap; MUST be the same function in the
