@@ -21,13 +21,39 @@ def _both(work, tag, *args):
     return read_outputs(out_s), read_outputs(out_c), info
 
 
+def _compare_with_racy_reference(work, tag, args, soft, cuda, keys=None):
+    """The soft side of this harness is the reference with its REAL thread pool, and that renderer races with itself: blocks of
+    different triangles test and write the same depth sample without ordering, so its own runs are not identical (measured here:
+    4 of 60 runs of the config-2 frame differ from the first one in one depth or colour sample).  RendererCUDA is deterministic.
+    So the bit-exact depth bar is kept, but a mismatch of a handful of samples gets the reference rendered again (twice at
+    most): a defect on the CUDA side fails every time, a lost update inside the reference does not repeat."""
+    from softglrender_b200.scene.trace import read_outputs
+    last = None
+    for attempt in range(3):
+        ref = soft if keys is None else {k: soft[k] for k in keys}
+        try:
+            return compare_outputs(ref, cuda)
+        except AssertionError as e:
+            last = e
+            racy = sum(int((soft[k].view(np.uint32) != cuda[k].view(np.uint32)).sum()) for k in ref if soft[k].dtype != np.uint8
+                       and k in cuda and soft[k].shape == cuda[k].shape)
+            if "depth samples differ" not in str(e) or racy > 8:
+                raise
+            out_s = os.path.join(work, "%s_soft_retry%d.out" % (tag, attempt))
+            run_viewer(work, "soft", out_s, *args)
+            soft = read_outputs(out_s)
+            os.remove(out_s)
+    raise last
+
+
 def test_config1_through_the_reference_viewer(work_dir):
     """BASELINE config 1: Cube forced to Blinn-Phong, 1000x800, no AA, shadow pass + main pass."""
     need_viewer()
     work = os.path.join(work_dir, "integ")
     os.makedirs(work, exist_ok=True)
-    soft, cuda, info = _both(work, "c1", "--model", "Cube", "--blinnphong", "--width", 1000, "--height", 800)
-    rep = compare_outputs(soft, cuda)
+    args = ("--model", "Cube", "--blinnphong", "--width", 1000, "--height", 800)
+    soft, cuda, info = _both(work, "c1", *args)
+    rep = _compare_with_racy_reference(work, "c1", args, soft, cuda)
     print("config 1 through the reference Viewer:", rep, info)
     assert soft["color"].std() > 5.0
     assert info["last_frame"]["kernel_launches"] > 0
@@ -43,7 +69,7 @@ def test_config2_through_the_reference_viewer_and_its_submission_matches_the_tra
     os.makedirs(work, exist_ok=True)
     args = ("--model", "DamagedHelmet", "--skybox", "Room", "--ibl", "--aa", "msaa", "--reverse-z", "--width", 960, "--height", 540)
     soft, cuda, info = _both(work, "c2", *args)
-    rep = compare_outputs({k: soft[k] for k in ("color", "depth.ms", "shadow")}, cuda)
+    rep = _compare_with_racy_reference(work, "c2", args, soft, cuda, keys=("color", "depth.ms", "shadow"))
     print("config 2 through the reference Viewer:", rep, info)
     # the Python scene builder's steady-state frame of the same configuration
     trace, data = workloads.build_c2(os.path.join(work_dir, "c2"), 960, 540)
