@@ -23,27 +23,34 @@ def _both(work, tag, *args):
 
 def _compare_with_racy_reference(work, tag, args, soft, cuda, keys=None):
     """The soft side of this harness is the reference with its REAL thread pool, and that renderer races with itself: blocks of
-    different triangles test and write the same depth sample without ordering, so its own runs are not identical (measured here:
-    4 of 60 runs of the config-2 frame differ from the first one in one depth or colour sample).  RendererCUDA is deterministic.
-    So the bit-exact depth bar is kept, but a mismatch of a handful of samples gets the reference rendered again (twice at
-    most): a defect on the CUDA side fails every time, a lost update inside the reference does not repeat."""
+    different triangles test and write the same depth sample without ordering, so its own runs are not identical (measured: 4 of
+    60 runs of the config-2 frame on 4 cores differ from the first one in one depth or colour sample, more often on the 16 cores
+    of the GPU box).  RendererCUDA is deterministic (tools/gpu/viewer_determinism.py: 80 runs over every scheduling variant,
+    byte-identical).  So the bit-exact depth bar is kept PER SAMPLE against the reference's consensus: a sample passes when it
+    equals the reference's value in at least one of up to five renders of the reference; a lost update inside the reference
+    moves from run to run, a defect on the CUDA side is wrong against every one of them.  At most 8 samples may need that."""
     from softglrender_b200.scene.trace import read_outputs
-    last = None
-    for attempt in range(3):
-        ref = soft if keys is None else {k: soft[k] for k in keys}
-        try:
-            return compare_outputs(ref, cuda)
-        except AssertionError as e:
-            last = e
-            racy = sum(int((soft[k].view(np.uint32) != cuda[k].view(np.uint32)).sum()) for k in ref if soft[k].dtype != np.uint8
-                       and k in cuda and soft[k].shape == cuda[k].shape)
-            if "depth samples differ" not in str(e) or racy > 8:
-                raise
-            out_s = os.path.join(work, "%s_soft_retry%d.out" % (tag, attempt))
-            run_viewer(work, "soft", out_s, *args)
-            soft = read_outputs(out_s)
-            os.remove(out_s)
-    raise last
+    keys = list(soft) if keys is None else list(keys)
+    depth_keys = [k for k in keys if soft[k].dtype != np.uint8]
+    for k in keys:
+        assert k in cuda and soft[k].shape == cuda[k].shape, (k, soft[k].shape, cuda.get(k, np.zeros(0)).shape)
+    matched = {k: soft[k].view(np.uint32) == cuda[k].view(np.uint32) for k in depth_keys}
+    first_miss = {k: int((~m).sum()) for k, m in matched.items()}
+    assert sum(first_miss.values()) <= 8, "depth differs from the reference in more than a racy handful of samples: %s" % first_miss
+    renders = 1
+    while not all(m.all() for m in matched.values()) and renders < 5:
+        out_s = os.path.join(work, "%s_soft_retry%d.out" % (tag, renders))
+        run_viewer(work, "soft", out_s, *args)
+        again = read_outputs(out_s)
+        os.remove(out_s)
+        for k in depth_keys:
+            matched[k] |= again[k].view(np.uint32) == cuda[k].view(np.uint32)
+        renders += 1
+    left = {k: int((~m).sum()) for k, m in matched.items()}
+    assert not any(left.values()), "depth samples that match none of %d reference renders: %s (first render: %s)" % (renders, left, first_miss)
+    rep = compare_outputs({k: soft[k] for k in keys if soft[k].dtype == np.uint8}, cuda)
+    rep["depth"] = dict(bit_exact_vs_consensus=True, reference_renders=renders, racy_samples_in_first_render=first_miss)
+    return rep
 
 
 def test_config1_through_the_reference_viewer(work_dir):
