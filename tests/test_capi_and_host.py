@@ -24,6 +24,23 @@ def test_header_symbols_exported():
     assert declared == set(capi.C_ABI_SYMBOLS), declared ^ set(capi.C_ABI_SYMBOLS)
 
 
+def test_ctypes_mirrors_have_the_sizes_of_the_header(tmp_path):
+    """The Python mirrors of the C ABI's structs (capi.py) are as large as the C compiler makes the header's: a field added on
+    one side only would shift every later counter silently."""
+    import shutil
+    import subprocess
+    from softglrender_b200 import capi
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "sglcuda.h"\nint main(void) { printf("%zu %zu\\n", sizeof(SglCounters), sizeof(SglKernelTime)); return 0; }\n')
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    c_counters, c_ktime = (int(x) for x in subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, check=True).stdout.split())
+    assert ctypes.sizeof(capi.SglCounters) == c_counters
+    assert ctypes.sizeof(capi.SglKernelTime) == c_ktime
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device sgl_init must fail loudly; the product has no CPU path."""
     import torch
