@@ -4,11 +4,16 @@
 // ModelLoader.cpp and assimp into a headless harness, which is how tests/test_viewer_integration*.py prove the drop-in.
 //
 // swapBuffer(): the software viewer uploads its CPU frame into a GL texture (ViewerSoftware.h:30-44).  Here the frame lives
-// in HBM; this header reads the resolved colour back into a host buffer (headless use, PNG dump, a GL upload by the
-// caller).  A windowed build would replace the read-back by CUDA-GL interop on outTexId_.
+// in HBM; this header reads the resolved colour back into a host buffer (headless use, PNG dump) and -- in a windowed build,
+// -DSGL_VIEWER_CUDA_PRESENT_GL, which is what the reference's main.cpp / ViewerManager needs -- hands it to the same GL
+// texture with the same glTexSubImage2D call as ViewerSoftware, so the imgui window presents it unchanged.  (CUDA-GL
+// interop on outTexId_ would save the PCIe round trip; the reference's present path is 8 MB per frame either way.)
 #pragma once
 #include <vector>
 #include "Viewer/Viewer.h"
+#ifdef SGL_VIEWER_CUDA_PRESENT_GL
+#include "Render/OpenGL/OpenGLUtils.h"
+#endif
 #include "Render/CUDA/RendererCUDA.h"
 
 namespace SoftGL {
@@ -26,6 +31,12 @@ class ViewerCUDA : public Viewer {
   int swapBuffer() override {
     auto *tex = dynamic_cast<TextureCUDA *>(texColorMain_.get());
     if (tex) tex->readPixels(0, 0, tex->multiSample ? 1 : 0, frame_, frameWidth_, frameHeight_);
+#ifdef SGL_VIEWER_CUDA_PRESENT_GL
+    if (tex && !frame_.empty()) {                        // ViewerSoftware.h:33-43, same target, same format
+      GL_CHECK(glBindTexture(GL_TEXTURE_2D, outTexId_));
+      GL_CHECK(glTexSubImage2D(GL_TEXTURE_2D, 0, 0, 0, frameWidth_, frameHeight_, GL_RGBA, GL_UNSIGNED_BYTE, frame_.data()));
+    }
+#endif
     return outTexId_;
   }
 

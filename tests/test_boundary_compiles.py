@@ -45,3 +45,21 @@ def test_interface_redeclaration_matches_reference_virtuals():
     for name in ("Renderer.h", "Texture.h", "Framebuffer.h", "Vertex.h", "Uniform.h", "ShaderProgram.h", "PipelineStates.h", "RenderStates.h"):
         theirs += virtual_dtors(open(os.path.join(REF, "src", "Render", name)).read())
     assert ours == sorted(set(theirs)), (ours, theirs)
+
+
+def test_viewer_cuda_compiles_headless_and_with_the_gl_present_path(tmp_path):
+    """ViewerCUDA against the reference's own Viewer.h: the headless form the integration harness links, and the windowed form
+    (-DSGL_VIEWER_CUDA_PRESENT_GL) that uploads the frame into the Viewer's GL texture exactly like ViewerSoftware::swapBuffer
+    (ViewerSoftware.h:30-44) -- compiled against the reference's vendored glad headers; there is no display here to run it."""
+    if not os.path.isdir(os.path.join(REF, "src", "Viewer")):
+        pytest.skip("reference tree not mounted")
+    tu = tmp_path / "viewer_cuda_tu.cpp"
+    tu.write_text('#include "Viewer/ViewerCUDA.h"\nint viewer_cuda_tu() { return sizeof(SoftGL::View::ViewerCUDA) > 0; }\n')
+    inc = [os.path.join(REF, "src"), os.path.join(REF, "src", "Viewer"), os.path.join(REF, "third_party", "glm"),
+           os.path.join(REF, "third_party", "glad", "include"), os.path.join(REF, "third_party", "json11"),
+           os.path.join(REF, "third_party", "imgui"), os.path.join(REF, "third_party", "assimp", "include"),
+           os.path.join(ROOT, "integration", "_build", "assimp", "include"), HOST, os.path.join(ROOT, "include")]
+    for defs in ([], ["-DSGL_VIEWER_CUDA_PRESENT_GL"]):
+        cmd = ["g++", "-std=gnu++11", "-fsyntax-only"] + defs + ["-I" + i for i in inc if os.path.isdir(i)] + [str(tu)]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, (defs, r.stdout[-3000:])
